@@ -1,0 +1,142 @@
+/*
+ * sph_b200.h -- C ABI of the B200-native SPH step engine (libsph_b200.so).
+ *
+ * This is the drop-in boundary for ONE hot path of iwoplaza/cuda-sph: the body of
+ *     VoxelSPHStrategy.compute_next_state(old_state) -> new_state
+ * (reference: sim/src/sph/strategies/abstract_sph_strategy.py:31-46 and voxel_sph_strategy.py:19-116, kernels in
+ * sim/src/sph/kernels/{voxel,base,util}_kernels.py).  Plain pointers and sizes only; no torch / numpy types.
+ * The reference binds it from Python with ctypes; the host-side mirror of the reference's
+ * strategy interface lives in cuda_sph_b200/strategy.py.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; sph_last_error() gives the message
+ *     (the reference raises Python exceptions: thread_layout.py:30-31, numba CudaAPIError).
+ *   - host arrays are C-contiguous; positions / velocities are (N,3) fp64 exactly like SimulationState
+ *     (common/data_classes.py:81-85).  The engine computes in fp32 (+ fp64 where parity needs it) and never keeps a
+ *     host pointer after the call returns (reference: copies to device, abstract_sph_strategy.py:66-67).
+ *   - one handle == one GPU == one CUDA stream; a handle is not thread-safe (the reference is single-threaded and
+ *     synchronises after every launch: abstract_sph_strategy.py:98,115).
+ *   - step calls are asynchronous on the handle's stream; download / get_* calls synchronise.
+ */
+#ifndef SPH_B200_H
+#define SPH_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPH_MODE_BOX 0   /* config.SIM_MODE == 'BOX'  -> collision_kernel_box  (base_kernels.py:75-98)  */
+#define SPH_MODE_PIPE 1  /* config.SIM_MODE == 'PIPE' -> collision_kernel      (base_kernels.py:56-72)  */
+
+#define SPH_FLAG_RECORD_NEIGHBOUR_COUNTS 1u /* density sweep also stores min(32, #in range) per particle (parity tap) */
+#define SPH_FLAG_RECORD_TERMS 2u            /* force sweep also stores the pressure and viscosity terms (parity tap)  */
+#define SPH_FLAG_NO_GRAPH 4u                /* launch kernels eagerly instead of replaying a CUDA graph             */
+
+/* Replaces: SimulationParameters (common/data_classes.py:70-78) + the module constants of config.py:18-36 that the
+ * reference freezes into its kernels at import time (base_kernels.py:2, voxel_kernels.py:5). */
+typedef struct SphParams {
+    int32_t particle_count;    /* params.particle_count                                   */
+    int32_t mode;              /* SPH_MODE_BOX | SPH_MODE_PIPE   (config.py:13)           */
+    double h;                  /* INF_R    config.py:20                                   */
+    double mass;               /* MASS     config.py:18                                   */
+    double rho0;               /* RHO_0    config.py:19                                   */
+    double k;                  /* K        config.py:22                                   */
+    double visc;               /* VISC     config.py:21                                   */
+    double damp;               /* DAMP     config.py:23                                   */
+    double dt;                 /* 1 / params.fps   abstract_sph_strategy.py:20            */
+    double external_force[3];  /* params.external_force                                   */
+    double space_size[3];      /* params.space_size                                       */
+    double voxel_size[3];      /* params.voxel_size                                       */
+    int32_t max_neighbours;    /* MAX_NEIGHBOURS config.py:30; only 32 is supported       */
+    uint32_t flags;            /* SPH_FLAG_*                                              */
+    uint64_t rng_seed;         /* 16435234 in abstract_sph_strategy.py:27                 */
+} SphParams;
+
+typedef struct SphEngine *sph_handle_t;
+
+/* Per-stage device time of the most recent sph_step_timed() call, milliseconds, summed over its steps. */
+typedef struct SphTimings {
+    float hash_ms;     /* assign_voxels_to_particles_kernel        voxel_kernels.py:88-105        */
+    float sort_ms;     /* host structured sort                     voxel_sph_strategy.py:81-88    */
+    float reorder_ms;  /* __populate_voxel_begins + SoA gather     voxel_sph_strategy.py:98-107   */
+    float density_ms;  /* density_kernel                           voxel_kernels.py:108-132       */
+    float force_ms;    /* pressure + viscosity + integrate + collide  voxel_kernels.py:135-211, base_kernels.py:30-98 */
+    float total_ms;
+    int32_t steps;
+    int32_t launches_per_step; /* kernels + memsets this library launches per step */
+} SphTimings;
+
+typedef struct SphStats {
+    int32_t n_particles;
+    int32_t n_dead;       /* particles in the "dead cell" (non-finite / out-of-table position) */
+    int32_t n_nonfinite;  /* particles with a non-finite position or velocity component                      */
+    int32_t n_cells;
+    float max_density;    /* analize.py:14 */
+    float max_speed;
+    int64_t steps_done;
+} SphStats;
+
+const char *sph_last_error(void);
+int sph_version(void);
+
+/* Replaces AbstractSPHStrategy.__init__ (abstract_sph_strategy.py:18-29): allocates device state, creates the
+ * xoroshiro128+ states (PIPE mode; numba create_xoroshiro128p_states(grid*block, seed)). */
+int sph_create(const SphParams *params, int device, sph_handle_t *out);
+int sph_destroy(sph_handle_t h);
+
+/* Replaces cuda.to_device(params.pipe.to_numpy()) (abstract_sph_strategy.py:74): rows x 5 table
+ * [x_start, y_c, z_c, r_start, length], last row = pipe end (common/data_classes.py:34-44). */
+int sph_set_pipe(sph_handle_t h, const double *table, int32_t rows);
+
+/* Use an existing CUDA stream (e.g. torch.cuda.current_stream().cuda_stream) instead of the engine's own. */
+int sph_set_stream(sph_handle_t h, void *cuda_stream);
+
+/* Replaces _send_arrays_to_gpu (abstract_sph_strategy.py:64-74): position, velocity (N,3) fp64 host arrays. */
+int sph_upload(sph_handle_t h, const double *position, const double *velocity);
+/* Same, from fp32 (N,3) host arrays (start states generated in fp32). */
+int sph_upload_f32(sph_handle_t h, const float *position, const float *velocity);
+
+/* n device-resident steps, no host round trip: hash -> sort -> cell table + SoA reorder -> density sweep ->
+ * fused pressure/viscosity/integrate/collide sweep.  Replaces the body of compute_next_state (:31-46) n times. */
+int sph_step(sph_handle_t h, int32_t n_steps);
+/* Same, launched eagerly with CUDA events around every stage; fills *t. */
+int sph_step_timed(sph_handle_t h, int32_t n_steps, SphTimings *t);
+
+/* Replaces __finalize_computation (abstract_sph_strategy.py:76-84): (N,3),(N,3),(N,) fp64, particle-id order.
+ * Any pointer may be NULL. */
+int sph_download(sph_handle_t h, double *position, double *velocity, double *density);
+int sph_download_f32(sph_handle_t h, float *position, float *velocity, float *density);
+
+/* The reference-facing call: upload + one step + download == compute_next_state(old_state). */
+int sph_compute_next_state(sph_handle_t h, const double *pos_in, const double *vel_in, double *pos_out,
+                           double *vel_out, double *density_out);
+
+int sph_sync(sph_handle_t h);
+
+/* ---- parity taps: state of the most recent step --------------------------------------------------------------- */
+int sph_get_keys(sph_handle_t h, int32_t *keys);                 /* self.voxels            voxel_sph_strategy.py:82 */
+int sph_get_sorted_ids(sph_handle_t h, int32_t *ids);            /* voxel_particle_map['particle_id']        :85-88 */
+int sph_get_sorted_keys(sph_handle_t h, int32_t *keys);          /* voxel_particle_map['voxel_id']           :85-88 */
+int sph_get_voxel_begin(sph_handle_t h, int32_t *begin, int64_t n_cells); /* self.voxel_begin (-1 = empty)  :92-107 */
+int sph_get_neighbour_counts(sph_handle_t h, int32_t *counts);   /* get_neighbours return value   voxel_kernels.py:85 */
+int sph_get_forces(sph_handle_t h, double *force);               /* self.result_force  abstract_sph_strategy.py:83 */
+int sph_get_terms(sph_handle_t h, double *pressure, double *viscosity); /* d_new_pressure_term / d_new_viscosity_term */
+int sph_get_rng_states(sph_handle_t h, uint64_t *states);        /* N x 2 uint64 (PIPE mode)                        */
+int sph_set_rng_states(sph_handle_t h, const uint64_t *states);
+int sph_get_stats(sph_handle_t h, SphStats *stats);
+int64_t sph_n_cells(sph_handle_t h);
+int sph_cell_dims(sph_handle_t h, int32_t *ceil3, int32_t *trunc3);
+
+/* Device pointers for zero-copy wrapping (torch / __cuda_array_interface__).  which: 0 = master position float4[N]
+ * (x,y,z,density), 1 = master velocity float4[N], 2 = sorted ids int32[N], 3 = sorted position float4[N]. */
+int sph_device_ptr(sph_handle_t h, int32_t which, void **ptr, int64_t *n_elements);
+
+/* Total kernels/memsets launched by this handle so far (bench.py's "gpu_launches"). */
+int64_t sph_launch_count(sph_handle_t h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPH_B200_H */
