@@ -1,0 +1,95 @@
+"""ctypes binding of libsph_b200.so (include/sph_b200.h).  There is no CPU fallback: a missing library or a missing
+GPU raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsph_b200.so")
+
+MODE_BOX, MODE_PIPE = 0, 1
+FLAG_RECORD_NEIGHBOUR_COUNTS, FLAG_RECORD_TERMS, FLAG_NO_GRAPH = 1, 2, 4
+
+
+class SphParams(C.Structure):
+    _fields_ = [("particle_count", C.c_int32), ("mode", C.c_int32), ("h", C.c_double), ("mass", C.c_double),
+                ("rho0", C.c_double), ("k", C.c_double), ("visc", C.c_double), ("damp", C.c_double),
+                ("dt", C.c_double), ("external_force", C.c_double * 3), ("space_size", C.c_double * 3),
+                ("voxel_size", C.c_double * 3), ("max_neighbours", C.c_int32), ("flags", C.c_uint32),
+                ("rng_seed", C.c_uint64)]
+
+
+class SphTimings(C.Structure):
+    _fields_ = [("hash_ms", C.c_float), ("sort_ms", C.c_float), ("reorder_ms", C.c_float),
+                ("density_ms", C.c_float), ("force_ms", C.c_float), ("total_ms", C.c_float), ("steps", C.c_int32),
+                ("launches_per_step", C.c_int32)]
+
+
+class SphStats(C.Structure):
+    _fields_ = [("n_particles", C.c_int32), ("n_dead", C.c_int32), ("n_nonfinite", C.c_int32),
+                ("n_cells", C.c_int32), ("max_density", C.c_float), ("max_speed", C.c_float),
+                ("steps_done", C.c_int64)]
+
+
+# every symbol include/sph_b200.h declares: name -> (restype, argtypes)
+_H = C.c_void_p
+_P = C.c_void_p
+EXPORTS = {
+    "sph_last_error": (C.c_char_p, []),
+    "sph_version": (C.c_int, []),
+    "sph_create": (C.c_int, [C.POINTER(SphParams), C.c_int, C.POINTER(_H)]),
+    "sph_destroy": (C.c_int, [_H]),
+    "sph_set_pipe": (C.c_int, [_H, _P, C.c_int32]),
+    "sph_set_stream": (C.c_int, [_H, _P]),
+    "sph_upload": (C.c_int, [_H, _P, _P]),
+    "sph_upload_f32": (C.c_int, [_H, _P, _P]),
+    "sph_step": (C.c_int, [_H, C.c_int32]),
+    "sph_step_timed": (C.c_int, [_H, C.c_int32, C.POINTER(SphTimings)]),
+    "sph_download": (C.c_int, [_H, _P, _P, _P]),
+    "sph_download_f32": (C.c_int, [_H, _P, _P, _P]),
+    "sph_compute_next_state": (C.c_int, [_H, _P, _P, _P, _P, _P]),
+    "sph_sync": (C.c_int, [_H]),
+    "sph_save_state": (C.c_int, [_H]),
+    "sph_restore_state": (C.c_int, [_H]),
+    "sph_get_keys": (C.c_int, [_H, _P]),
+    "sph_get_sorted_ids": (C.c_int, [_H, _P]),
+    "sph_get_sorted_keys": (C.c_int, [_H, _P]),
+    "sph_get_voxel_begin": (C.c_int, [_H, _P, C.c_int64]),
+    "sph_get_neighbour_counts": (C.c_int, [_H, _P]),
+    "sph_get_forces": (C.c_int, [_H, _P]),
+    "sph_get_terms": (C.c_int, [_H, _P, _P]),
+    "sph_get_rng_states": (C.c_int, [_H, _P]),
+    "sph_set_rng_states": (C.c_int, [_H, _P]),
+    "sph_get_stats": (C.c_int, [_H, C.POINTER(SphStats)]),
+    "sph_n_cells": (C.c_int64, [_H]),
+    "sph_cell_dims": (C.c_int, [_H, _P, _P]),
+    "sph_device_ptr": (C.c_int, [_H, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
+    "sph_launch_count": (C.c_int64, [_H]),
+}
+
+_lib = None
+
+
+class SphError(RuntimeError):
+    pass
+
+
+def load():
+    """Load libsph_b200.so; raises if it has not been built (python -m cuda_sph_b200.build)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise SphError(f"{LIB_PATH} is missing: build it with `python -m cuda_sph_b200.build` "
+                           "(there is no CPU fallback)")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in EXPORTS.items():
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = lib
+    return _lib
+
+
+def check(rc: int):
+    if rc != 0:
+        raise SphError(load().sph_last_error().decode())

@@ -1,0 +1,633 @@
+// libsph_b200.so -- engine object + C ABI (include/sph_b200.h).  One handle = one GPU = one stream.
+//
+// Step pipeline (device resident, replayed as a CUDA graph):
+//   hash_kernel -> [rs_hist, rs_scan, rs_scatter] x passes -> memset(cell_range) -> reorder_kernel
+//   -> density_kernel -> force_kernel (pressure + viscosity + integrate + collide, scatter to master)
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/sph_b200.h"
+#include "radix_sort.cuh"
+#include "sph_kernels.cuh"
+#include "sweep.cuh"
+
+using namespace sph;
+
+static thread_local std::string g_err;
+static int fail(const std::string &m) {
+    g_err = m;
+    return 1;
+}
+#define CK(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess)                                                                           \
+            return fail(std::string(#call) + ": " + cudaGetErrorString(e_) + " (" __FILE__ ":" +         \
+                        std::to_string(__LINE__) + ")");                                                 \
+    } while (0)
+
+struct SphEngine {
+    SphParams p{};
+    int device = 0;
+    int n = 0;
+    GridDesc grid{};
+    StepConsts consts{};
+    int32_t ceil_dims[3]{}, trunc_dims[3]{};
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+
+    // master (id order) and sorted (cell order) state
+    float4 *pos_m = nullptr, *vel_m = nullptr, *spos = nullptr, *svel = nullptr, *sforce = nullptr;
+    float4 *spress = nullptr, *svisc = nullptr;
+    float *srho = nullptr;
+    uint16_t *nlist = nullptr;   // [n][32] neighbour lists (virtual-list indices), density -> force
+    uint8_t *ncnt = nullptr;     // [n] neighbour counts
+    // keys / sort buffers
+    uint32_t *keys = nullptr, *ka = nullptr, *va = nullptr, *kb = nullptr, *vb = nullptr;
+    uint32_t *skeys = nullptr, *sids = nullptr;  // aliases of the final sort buffers
+    uint32_t *block_hist = nullptr, *digit_total = nullptr;
+    int ntiles = 0, passes = 0, pass_bits[8]{}, key_bits = 0;
+    int2 *cell_range = nullptr;
+    // pipe
+    double *pipe_d = nullptr;
+    int pipe_rows = 0;
+    uint64_t *rng = nullptr;
+    // host-boundary staging (fp64 / fp32 (N,3) + rho), grown lazily
+    void *stage = nullptr;
+    size_t stage_bytes = 0;
+    uint32_t *stats_d = nullptr;
+    // snapshot (sph_save_state)
+    float4 *snap_pos = nullptr, *snap_vel = nullptr;
+    uint64_t *snap_rng = nullptr;
+    int64_t snap_steps = -1;
+    // graph
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t graph_exec = nullptr;
+    bool graph_valid = false;
+    // events for sph_step_timed
+    cudaEvent_t ev[8]{};
+    bool has_state = false;
+    int64_t steps_done = 0;
+    int64_t launches = 0;
+    int launches_per_step = 0;
+};
+
+const char *sph_last_error(void) { return g_err.c_str(); }
+int sph_version(void) { return 1; }
+
+static int ensure_stage(SphEngine *e, size_t bytes) {
+    if (e->stage_bytes >= bytes) return 0;
+    if (e->stage) cudaFree(e->stage);
+    e->stage = nullptr;
+    e->stage_bytes = 0;
+    CK(cudaMalloc(&e->stage, bytes));
+    e->stage_bytes = bytes;
+    return 0;
+}
+
+static void invalidate_graph(SphEngine *e) {
+    if (e->graph_exec) cudaGraphExecDestroy(e->graph_exec);
+    if (e->graph) cudaGraphDestroy(e->graph);
+    e->graph_exec = nullptr;
+    e->graph = nullptr;
+    e->graph_valid = false;
+}
+
+// numba create_xoroshiro128p_states: state 0 = SplitMix64(seed) in both words, state i = state i-1 jumped 2^64.
+static void init_rng_host(std::vector<uint64_t> &st, int64_t n, uint64_t seed) {
+    st.resize(2 * (size_t)n);
+    if (n < 1) return;
+    uint64_t z = seed + 0x9E3779B97F4A7C15ULL;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    z ^= z >> 31;
+    uint64_t s0 = z, s1 = z;
+    st[0] = s0;
+    st[1] = s1;
+    static const uint64_t J[2] = {0xbeac0467eba5facbULL, 0xd86b048b86aa9922ULL};
+    for (int64_t i = 1; i < n; ++i) {
+        uint64_t a = 0, b = 0;
+        for (int w = 0; w < 2; ++w)
+            for (int bit = 0; bit < 64; ++bit) {
+                if (J[w] & (1ULL << bit)) { a ^= s0; b ^= s1; }
+                xoro_next(s0, s1);
+            }
+        s0 = a;
+        s1 = b;
+        st[2 * i] = s0;
+        st[2 * i + 1] = s1;
+    }
+}
+
+static int validate(const SphParams *p) {
+    if (!p) return fail("params is NULL");
+    if (p->particle_count <= 0) return fail("particle_count must be > 0");
+    if (p->max_neighbours != kMaxNeighbours) return fail("only max_neighbours == 32 is supported");
+    if (p->mode != SPH_MODE_BOX && p->mode != SPH_MODE_PIPE) return fail("mode must be SPH_MODE_BOX or SPH_MODE_PIPE");
+    if (!(p->h > 0) || !(p->dt > 0)) return fail("h and dt must be > 0");
+    for (int d = 0; d < 3; ++d)
+        if (!(p->voxel_size[d] > 0) || !(p->space_size[d] > 0)) return fail("space_size / voxel_size must be > 0");
+    return 0;
+}
+
+int sph_create(const SphParams *params, int device, sph_handle_t *out) {
+    if (!out) return fail("out is NULL");
+    *out = nullptr;
+    if (validate(params)) return 1;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail("no CUDA device: libsph_b200 has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail("bad device index");
+    CK(cudaSetDevice(device));
+
+    SphEngine *e = new SphEngine();
+    e->p = *params;
+    e->device = device;
+    e->n = params->particle_count;
+    const int n = e->n;
+
+    // grid: ceil dims for keys, trunc dims for the neighbour walk (reference quirk Q2)
+    long long ncells = 1;
+    for (int d = 0; d < 3; ++d) {
+        const double q = params->space_size[d] / params->voxel_size[d];
+        e->ceil_dims[d] = (int32_t)std::ceil(q);
+        e->trunc_dims[d] = (int32_t)q;
+        e->grid.voxel[d] = params->voxel_size[d];
+        ncells *= e->ceil_dims[d];
+    }
+    if (ncells <= 0 || ncells >= (1LL << 31) - 2) {
+        delete e;
+        return fail("cell table too large for int32 keys");
+    }
+    e->grid.xoff = 0;
+    e->grid.wk = e->ceil_dims[0];
+    e->grid.hk = e->ceil_dims[1];
+    e->grid.wn = e->trunc_dims[0];
+    e->grid.hn = e->trunc_dims[1];
+    e->grid.tx = e->trunc_dims[0];
+    e->grid.ty = e->trunc_dims[1];
+    e->grid.tz = e->trunc_dims[2];
+    e->grid.ncells = (int32_t)ncells;
+
+    // constants (config.py:24-29)
+    const double h = params->h;
+    StepConsts &c = e->consts;
+    c.h = (float)h;
+    c.h2 = (float)(h * h);
+    c.h2_lo = (float)(h * h * (1.0 - 1e-5));
+    c.h2_hi = (float)(h * h * (1.0 + 1e-5));
+    c.w_mass = (float)(315.0 / (64.0 * M_PI * std::pow(h, 9.0)) * params->mass);
+    c.grad_c = (float)(-45.0 / (M_PI * std::pow(h, 6.0)));
+    c.lap_c = (float)(45.0 / (M_PI * std::pow(h, 6.0)));
+    c.k = (float)params->k;
+    c.rho0 = (float)params->rho0;
+    c.mass_visc = (float)(params->mass * params->visc);
+    // largest double r2 with sqrt(r2) <= h  (sqrt is correctly rounded and monotone)
+    double r2m = h * h;
+    while (std::sqrt(std::nextafter(r2m, INFINITY)) <= h) r2m = std::nextafter(r2m, INFINITY);
+    while (std::sqrt(r2m) > h) r2m = std::nextafter(r2m, -INFINITY);
+    c.r2_max = r2m;
+    c.dt = params->dt;
+    c.damp = params->damp;
+    for (int d = 0; d < 3; ++d) {
+        c.ext[d] = params->external_force[d];
+        c.space[d] = params->space_size[d];
+    }
+    c.mode = params->mode;
+    c.pipe_rows = 0;
+
+    // radix passes over the bits of [0, ncells] (ncells itself = dead cell)
+    int bits = 1;
+    while ((1LL << bits) <= ncells) ++bits;
+    e->key_bits = bits;
+    e->passes = (bits + 7) / 8;
+    for (int i = 0; i < e->passes; ++i) e->pass_bits[i] = bits / e->passes + (i < bits % e->passes ? 1 : 0);
+    e->ntiles = (n + RS_TILE - 1) / RS_TILE;
+
+#define ALLOC(ptr, count)                                                                   \
+    do {                                                                                    \
+        cudaError_t e_ = cudaMalloc((void **)&(ptr), sizeof(*(ptr)) * (size_t)(count));     \
+        if (e_ != cudaSuccess) {                                                            \
+            fail(std::string("cudaMalloc " #ptr ": ") + cudaGetErrorString(e_));            \
+            sph_destroy(e);                                                                 \
+            return 1;                                                                       \
+        }                                                                                   \
+    } while (0)
+    ALLOC(e->pos_m, n);
+    ALLOC(e->vel_m, n);
+    ALLOC(e->spos, n);
+    ALLOC(e->svel, n);
+    ALLOC(e->sforce, n);
+    ALLOC(e->srho, n);
+    ALLOC(e->keys, n);
+    ALLOC(e->ka, n);
+    ALLOC(e->va, n);
+    ALLOC(e->kb, n);
+    ALLOC(e->vb, n);
+    ALLOC(e->block_hist, (size_t)RS_RADIX * e->ntiles);
+    ALLOC(e->digit_total, RS_RADIX);
+    ALLOC(e->cell_range, ncells + 1);
+    ALLOC(e->stats_d, 4);
+    ALLOC(e->nlist, (size_t)n * 32);
+    ALLOC(e->ncnt, n);
+    if (params->flags & SPH_FLAG_RECORD_TERMS) {
+        ALLOC(e->spress, n);
+        ALLOC(e->svisc, n);
+    }
+    if (params->mode == SPH_MODE_PIPE) {
+        ALLOC(e->rng, 2 * (size_t)n);
+        std::vector<uint64_t> st;
+        init_rng_host(st, n, params->rng_seed);
+        if (cudaMemcpy(e->rng, st.data(), st.size() * sizeof(uint64_t), cudaMemcpyHostToDevice) != cudaSuccess) {
+            sph_destroy(e);
+            return fail("rng upload failed");
+        }
+    }
+#undef ALLOC
+    // final sort output buffer: pass 0 writes A, pass 1 writes B, ...
+    const bool final_in_a = (e->passes % 2) == 1;
+    e->skeys = final_in_a ? e->ka : e->kb;
+    e->sids = final_in_a ? e->va : e->vb;
+
+    cudaMemset(e->pos_m, 0, sizeof(float4) * (size_t)n);
+    cudaMemset(e->vel_m, 0, sizeof(float4) * (size_t)n);
+    cudaMemset(e->sforce, 0, sizeof(float4) * (size_t)n);
+    cudaMemset(e->srho, 0, sizeof(float) * (size_t)n);
+    cudaMemset(e->keys, 0, sizeof(uint32_t) * (size_t)n);
+    cudaMemset(e->cell_range, 0, sizeof(int2) * (size_t)(ncells + 1));
+    if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        sph_destroy(e);
+        return fail("cudaStreamCreate failed");
+    }
+    e->own_stream = true;
+    for (auto &ev : e->ev) cudaEventCreate(&ev);
+    e->launches_per_step = 1 + 3 * e->passes + 1 + 1 + 1 + 1;
+    if (cudaDeviceSynchronize() != cudaSuccess) {
+        sph_destroy(e);
+        return fail("device error during create");
+    }
+    *out = e;
+    return 0;
+}
+
+int sph_destroy(sph_handle_t e) {
+    if (!e) return 0;
+    cudaSetDevice(e->device);
+    cudaDeviceSynchronize();
+    invalidate_graph(e);
+    void *ptrs[] = {e->pos_m, e->vel_m, e->spos, e->svel, e->sforce, e->spress, e->svisc, e->srho, e->nlist, e->ncnt,
+                    e->keys, e->ka, e->va, e->kb, e->vb, e->block_hist, e->digit_total, e->cell_range, e->pipe_d,
+                    e->rng, e->stage, e->stats_d, e->snap_pos, e->snap_vel, e->snap_rng};
+    for (void *q : ptrs)
+        if (q) cudaFree(q);
+    for (auto &ev : e->ev)
+        if (ev) cudaEventDestroy(ev);
+    if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+    return 0;
+}
+
+int sph_set_stream(sph_handle_t e, void *cuda_stream) {
+    if (!e) return fail("null handle");
+    CK(cudaSetDevice(e->device));
+    CK(cudaStreamSynchronize(e->stream));
+    if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
+    e->stream = (cudaStream_t)cuda_stream;
+    e->own_stream = false;
+    invalidate_graph(e);
+    return 0;
+}
+
+int sph_set_pipe(sph_handle_t e, const double *table, int32_t rows) {
+    if (!e) return fail("null handle");
+    if (rows < 2 || !table) return fail("pipe table needs >= 2 rows of 5 doubles");
+    CK(cudaSetDevice(e->device));
+    CK(cudaStreamSynchronize(e->stream));
+    if (e->pipe_d) cudaFree(e->pipe_d);
+    e->pipe_d = nullptr;
+    CK(cudaMalloc((void **)&e->pipe_d, sizeof(double) * 5 * (size_t)rows));
+    CK(cudaMemcpy(e->pipe_d, table, sizeof(double) * 5 * (size_t)rows, cudaMemcpyHostToDevice));
+    e->pipe_rows = rows;
+    e->consts.pipe_rows = rows;
+    invalidate_graph(e);
+    return 0;
+}
+
+template <typename T>
+static int upload_impl(SphEngine *e, const T *pos, const T *vel) {
+    if (!e) return fail("null handle");
+    if (!pos || !vel) return fail("position / velocity is NULL");
+    CK(cudaSetDevice(e->device));
+    const size_t n = e->n, bytes = 3 * n * sizeof(T);
+    if (ensure_stage(e, 7 * n * sizeof(double))) return 1;
+    T *dpos = (T *)e->stage, *dvel = dpos + 3 * n;
+    CK(cudaMemcpyAsync(dpos, pos, bytes, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(dvel, vel, bytes, cudaMemcpyHostToDevice, e->stream));
+    pack_state_kernel<T><<<(e->n + 255) / 256, 256, 0, e->stream>>>(dpos, dvel, e->pos_m, e->vel_m, e->n);
+    CK(cudaGetLastError());
+    e->launches += 1;
+    e->has_state = true;
+    return 0;
+}
+int sph_upload(sph_handle_t e, const double *pos, const double *vel) { return upload_impl<double>(e, pos, vel); }
+int sph_upload_f32(sph_handle_t e, const float *pos, const float *vel) { return upload_impl<float>(e, pos, vel); }
+
+template <typename T>
+static int download_impl(SphEngine *e, T *pos, T *vel, T *rho) {
+    if (!e) return fail("null handle");
+    CK(cudaSetDevice(e->device));
+    const size_t n = e->n;
+    if (ensure_stage(e, 7 * n * sizeof(double))) return 1;
+    T *dpos = (T *)e->stage, *dvel = dpos + 3 * n, *drho = dvel + 3 * n;
+    unpack_state_kernel<T><<<(e->n + 255) / 256, 256, 0, e->stream>>>(e->pos_m, e->vel_m, pos ? dpos : nullptr,
+                                                                       vel ? dvel : nullptr, rho ? drho : nullptr,
+                                                                       e->n);
+    CK(cudaGetLastError());
+    e->launches += 1;
+    if (pos) CK(cudaMemcpyAsync(pos, dpos, 3 * n * sizeof(T), cudaMemcpyDeviceToHost, e->stream));
+    if (vel) CK(cudaMemcpyAsync(vel, dvel, 3 * n * sizeof(T), cudaMemcpyDeviceToHost, e->stream));
+    if (rho) CK(cudaMemcpyAsync(rho, drho, n * sizeof(T), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+int sph_download(sph_handle_t e, double *p, double *v, double *r) { return download_impl<double>(e, p, v, r); }
+int sph_download_f32(sph_handle_t e, float *p, float *v, float *r) { return download_impl<float>(e, p, v, r); }
+
+// Enqueue one step on e->stream.  If evs != nullptr, records stage boundaries into e->ev[0..5].
+static int enqueue_step(SphEngine *e, bool timed) {
+    const int n = e->n;
+    cudaStream_t s = e->stream;
+    const int g256 = (n + 255) / 256;
+    if (timed) cudaEventRecord(e->ev[0], s);
+    hash_kernel<<<g256, 256, 0, s>>>(e->pos_m, e->keys, n, e->grid);
+    if (timed) cudaEventRecord(e->ev[1], s);
+    // LSD radix sort of (key, id): pass 0 reads keys with implicit iota values
+    {
+        const uint32_t *kin = e->keys, *vin = nullptr;
+        int shift = 0;
+        for (int p = 0; p < e->passes; ++p) {
+            uint32_t *kout = (p % 2 == 0) ? e->ka : e->kb;
+            uint32_t *vout = (p % 2 == 0) ? e->va : e->vb;
+            const uint32_t mask = (1u << e->pass_bits[p]) - 1u;
+            rs_hist<<<e->ntiles, RS_THREADS, 0, s>>>(kin, n, shift, mask, e->block_hist, e->ntiles);
+            rs_scan<<<RS_RADIX, RS_THREADS, 0, s>>>(e->block_hist, e->ntiles, e->digit_total);
+            rs_scatter<<<e->ntiles, RS_THREADS, 0, s>>>(kin, vin, kout, vout, n, shift, mask, e->block_hist,
+                                                        e->ntiles, e->digit_total);
+            kin = kout;
+            vin = vout;
+            shift += e->pass_bits[p];
+        }
+    }
+    if (timed) cudaEventRecord(e->ev[2], s);
+    cudaMemsetAsync(e->cell_range, 0, sizeof(int2) * ((size_t)e->grid.ncells + 1), s);
+    reorder_kernel<<<g256, 256, 0, s>>>(e->skeys, e->sids, e->pos_m, e->vel_m, e->spos, e->svel, e->cell_range, n);
+    if (timed) cudaEventRecord(e->ev[3], s);
+    SweepArgs sa{};
+    sa.spos = e->spos;
+    sa.svel = e->svel;
+    sa.skeys = e->skeys;
+    sa.sids = e->sids;
+    sa.cell_range = e->cell_range;
+    sa.srho = e->srho;
+    sa.nlist = e->nlist;
+    sa.ncnt = e->ncnt;
+    sa.pos_m = e->pos_m;
+    sa.vel_m = e->vel_m;
+    sa.sforce = e->sforce;
+    sa.spress = e->spress;
+    sa.svisc = e->svisc;
+    sa.pipe = e->pipe_d;
+    sa.rng = e->rng;
+    sa.n = n;
+    const int gsw = (n + SW_THREADS - 1) / SW_THREADS;
+    density_kernel<<<gsw, SW_THREADS, 0, s>>>(sa, e->grid, e->consts);
+    if (timed) cudaEventRecord(e->ev[4], s);
+    if (e->spress)
+        force_kernel<true><<<gsw, SW_THREADS, 0, s>>>(sa, e->grid, e->consts);
+    else
+        force_kernel<false><<<gsw, SW_THREADS, 0, s>>>(sa, e->grid, e->consts);
+    if (timed) cudaEventRecord(e->ev[5], s);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+static int check_ready(SphEngine *e) {
+    if (!e) return fail("null handle");
+    if (!e->has_state) return fail("no particle state: call sph_upload first");
+    if (e->p.mode == SPH_MODE_PIPE && !e->pipe_d) return fail("PIPE mode needs sph_set_pipe before stepping");
+    return 0;
+}
+
+int sph_step(sph_handle_t e, int32_t n_steps) {
+    if (check_ready(e)) return 1;
+    if (n_steps <= 0) return 0;
+    CK(cudaSetDevice(e->device));
+    if (e->p.flags & SPH_FLAG_NO_GRAPH) {
+        for (int i = 0; i < n_steps; ++i)
+            if (enqueue_step(e, false)) return 1;
+    } else {
+        if (!e->graph_valid) {
+            CK(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
+            const int rc = enqueue_step(e, false);
+            cudaGraph_t g = nullptr;
+            cudaError_t ce = cudaStreamEndCapture(e->stream, &g);
+            if (rc) return 1;
+            if (ce != cudaSuccess) return fail(std::string("graph capture: ") + cudaGetErrorString(ce));
+            e->graph = g;
+            CK(cudaGraphInstantiate(&e->graph_exec, e->graph, 0));
+            e->graph_valid = true;
+        }
+        for (int i = 0; i < n_steps; ++i) CK(cudaGraphLaunch(e->graph_exec, e->stream));
+    }
+    e->steps_done += n_steps;
+    e->launches += (int64_t)n_steps * e->launches_per_step;
+    return 0;
+}
+
+int sph_step_timed(sph_handle_t e, int32_t n_steps, SphTimings *t) {
+    if (check_ready(e)) return 1;
+    if (!t) return fail("timings is NULL");
+    CK(cudaSetDevice(e->device));
+    memset(t, 0, sizeof(*t));
+    for (int i = 0; i < n_steps; ++i) {
+        if (enqueue_step(e, true)) return 1;
+        CK(cudaEventSynchronize(e->ev[5]));
+        float ms[5];
+        for (int k = 0; k < 5; ++k) CK(cudaEventElapsedTime(&ms[k], e->ev[k], e->ev[k + 1]));
+        t->hash_ms += ms[0];
+        t->sort_ms += ms[1];
+        t->reorder_ms += ms[2];
+        t->density_ms += ms[3];
+        t->force_ms += ms[4];
+        float tot;
+        CK(cudaEventElapsedTime(&tot, e->ev[0], e->ev[5]));
+        t->total_ms += tot;
+    }
+    t->steps = n_steps;
+    t->launches_per_step = e->launches_per_step;
+    e->steps_done += n_steps;
+    e->launches += (int64_t)n_steps * e->launches_per_step;
+    return 0;
+}
+
+int sph_compute_next_state(sph_handle_t e, const double *pos_in, const double *vel_in, double *pos_out,
+                           double *vel_out, double *density_out) {
+    if (sph_upload(e, pos_in, vel_in)) return 1;
+    if (sph_step(e, 1)) return 1;
+    return sph_download(e, pos_out, vel_out, density_out);
+}
+
+int sph_save_state(sph_handle_t e) {
+    if (!e) return fail("null handle");
+    if (!e->has_state) return fail("no particle state to save");
+    CK(cudaSetDevice(e->device));
+    const size_t n = e->n;
+    if (!e->snap_pos) CK(cudaMalloc((void **)&e->snap_pos, sizeof(float4) * n));
+    if (!e->snap_vel) CK(cudaMalloc((void **)&e->snap_vel, sizeof(float4) * n));
+    if (e->rng && !e->snap_rng) CK(cudaMalloc((void **)&e->snap_rng, 2 * sizeof(uint64_t) * n));
+    CK(cudaMemcpyAsync(e->snap_pos, e->pos_m, sizeof(float4) * n, cudaMemcpyDeviceToDevice, e->stream));
+    CK(cudaMemcpyAsync(e->snap_vel, e->vel_m, sizeof(float4) * n, cudaMemcpyDeviceToDevice, e->stream));
+    if (e->rng)
+        CK(cudaMemcpyAsync(e->snap_rng, e->rng, 2 * sizeof(uint64_t) * n, cudaMemcpyDeviceToDevice, e->stream));
+    e->snap_steps = e->steps_done;
+    return 0;
+}
+
+int sph_restore_state(sph_handle_t e) {
+    if (!e) return fail("null handle");
+    if (e->snap_steps < 0) return fail("sph_save_state has not been called");
+    CK(cudaSetDevice(e->device));
+    const size_t n = e->n;
+    CK(cudaMemcpyAsync(e->pos_m, e->snap_pos, sizeof(float4) * n, cudaMemcpyDeviceToDevice, e->stream));
+    CK(cudaMemcpyAsync(e->vel_m, e->snap_vel, sizeof(float4) * n, cudaMemcpyDeviceToDevice, e->stream));
+    if (e->rng)
+        CK(cudaMemcpyAsync(e->rng, e->snap_rng, 2 * sizeof(uint64_t) * n, cudaMemcpyDeviceToDevice, e->stream));
+    e->steps_done = e->snap_steps;
+    return 0;
+}
+
+int sph_sync(sph_handle_t e) {
+    if (!e) return fail("null handle");
+    CK(cudaSetDevice(e->device));
+    CK(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+// ---- parity taps ----------------------------------------------------------------------------------------------
+static int d2h(SphEngine *e, void *dst, const void *src, size_t bytes) {
+    CK(cudaSetDevice(e->device));
+    CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+int sph_get_keys(sph_handle_t e, int32_t *keys) {
+    if (!e || !keys) return fail("null argument");
+    return d2h(e, keys, e->keys, sizeof(int32_t) * (size_t)e->n);
+}
+int sph_get_sorted_ids(sph_handle_t e, int32_t *ids) {
+    if (!e || !ids) return fail("null argument");
+    return d2h(e, ids, e->sids, sizeof(int32_t) * (size_t)e->n);
+}
+int sph_get_sorted_keys(sph_handle_t e, int32_t *keys) {
+    if (!e || !keys) return fail("null argument");
+    return d2h(e, keys, e->skeys, sizeof(int32_t) * (size_t)e->n);
+}
+int sph_get_voxel_begin(sph_handle_t e, int32_t *begin, int64_t n_cells) {
+    if (!e || !begin) return fail("null argument");
+    if (n_cells != e->grid.ncells) return fail("n_cells mismatch (use sph_n_cells)");
+    CK(cudaSetDevice(e->device));
+    if (ensure_stage(e, sizeof(int32_t) * (size_t)n_cells)) return 1;
+    voxel_begin_kernel<<<(int)((n_cells + 255) / 256), 256, 0, e->stream>>>(e->cell_range, (int32_t *)e->stage,
+                                                                            (int)n_cells);
+    CK(cudaGetLastError());
+    return d2h(e, begin, e->stage, sizeof(int32_t) * (size_t)n_cells);
+}
+int sph_get_neighbour_counts(sph_handle_t e, int32_t *counts) {
+    if (!e || !counts) return fail("null argument");
+    if (e->steps_done == 0) return fail("no step has run yet");
+    CK(cudaSetDevice(e->device));
+    if (ensure_stage(e, sizeof(int32_t) * (size_t)e->n)) return 1;
+    unsort_count_kernel<<<(e->n + 255) / 256, 256, 0, e->stream>>>(e->ncnt, e->sids, (int32_t *)e->stage, e->n);
+    CK(cudaGetLastError());
+    return d2h(e, counts, e->stage, sizeof(int32_t) * (size_t)e->n);
+}
+static int get_vec3(SphEngine *e, const float4 *sorted, double *out) {
+    CK(cudaSetDevice(e->device));
+    if (ensure_stage(e, 7 * sizeof(double) * (size_t)e->n)) return 1;
+    unsort_vec3_kernel<<<(e->n + 255) / 256, 256, 0, e->stream>>>(sorted, e->sids, (double *)e->stage, e->n);
+    CK(cudaGetLastError());
+    return d2h(e, out, e->stage, 3 * sizeof(double) * (size_t)e->n);
+}
+int sph_get_forces(sph_handle_t e, double *force) {
+    if (!e || !force) return fail("null argument");
+    if (e->steps_done == 0) return fail("no step has run yet");
+    return get_vec3(e, e->sforce, force);
+}
+int sph_get_terms(sph_handle_t e, double *pressure, double *viscosity) {
+    if (!e) return fail("null handle");
+    if (!e->spress) return fail("create the engine with SPH_FLAG_RECORD_TERMS");
+    if (e->steps_done == 0) return fail("no step has run yet");
+    if (pressure && get_vec3(e, e->spress, pressure)) return 1;
+    if (viscosity && get_vec3(e, e->svisc, viscosity)) return 1;
+    return 0;
+}
+int sph_get_rng_states(sph_handle_t e, uint64_t *states) {
+    if (!e || !states) return fail("null argument");
+    if (!e->rng) return fail("rng states exist in PIPE mode only");
+    return d2h(e, states, e->rng, 2 * sizeof(uint64_t) * (size_t)e->n);
+}
+int sph_set_rng_states(sph_handle_t e, const uint64_t *states) {
+    if (!e || !states) return fail("null argument");
+    if (!e->rng) return fail("rng states exist in PIPE mode only");
+    CK(cudaSetDevice(e->device));
+    CK(cudaMemcpyAsync(e->rng, states, 2 * sizeof(uint64_t) * (size_t)e->n, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+int sph_get_stats(sph_handle_t e, SphStats *st) {
+    if (!e || !st) return fail("null argument");
+    CK(cudaSetDevice(e->device));
+    CK(cudaMemsetAsync(e->stats_d, 0, 4 * sizeof(uint32_t), e->stream));
+    stats_kernel<<<(e->n + 255) / 256, 256, 0, e->stream>>>(e->pos_m, e->vel_m, e->n, e->stats_d);
+    CK(cudaGetLastError());
+    uint32_t h[4];
+    int2 dead{0, 0};
+    CK(cudaMemcpyAsync(h, e->stats_d, sizeof(h), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpyAsync(&dead, e->cell_range + e->grid.ncells, sizeof(int2), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    st->n_particles = e->n;
+    st->n_dead = dead.y - dead.x;
+    st->n_nonfinite = (int32_t)h[0];
+    st->n_cells = e->grid.ncells;
+    memcpy(&st->max_density, &h[1], 4);
+    memcpy(&st->max_speed, &h[2], 4);
+    st->steps_done = e->steps_done;
+    return 0;
+}
+int64_t sph_n_cells(sph_handle_t e) { return e ? e->grid.ncells : -1; }
+int sph_cell_dims(sph_handle_t e, int32_t *ceil3, int32_t *trunc3) {
+    if (!e) return fail("null handle");
+    for (int d = 0; d < 3; ++d) {
+        if (ceil3) ceil3[d] = e->ceil_dims[d];
+        if (trunc3) trunc3[d] = e->trunc_dims[d];
+    }
+    return 0;
+}
+int sph_device_ptr(sph_handle_t e, int32_t which, void **ptr, int64_t *n_elements) {
+    if (!e || !ptr) return fail("null argument");
+    void *q = nullptr;
+    switch (which) {
+        case 0: q = e->pos_m; break;
+        case 1: q = e->vel_m; break;
+        case 2: q = e->sids; break;
+        case 3: q = e->spos; break;
+        default: return fail("unknown buffer id");
+    }
+    *ptr = q;
+    if (n_elements) *n_elements = e->n;
+    return 0;
+}
+int64_t sph_launch_count(sph_handle_t e) { return e ? e->launches : -1; }

@@ -1,0 +1,137 @@
+// SPH step kernels (sm_100a) other than the neighbour sweeps (sweep.cuh): cell hashing, cell table + SoA reorder,
+// the fp64 <-> fp32 state converters at the host boundary and the parity-tap helpers.
+//
+// Data layout in HBM:
+//   master  pos_m[N] float4 (x, y, z, density), vel_m[N] float4 (vx, vy, vz, 0)      -- particle-id order
+//   sorted  spos[N]  float4 (x, y, z, -),       svel[N]  float4, srho[N] float        -- cell-contiguous order
+//   cells   cell_range[ncells + 1] int2 (begin, end) into the sorted arrays; entry ncells is the dead cell
+#pragma once
+#include "collide.cuh"
+#include "sph_common.cuh"
+
+namespace sph {
+
+// ---- assign_voxels_to_particles_kernel (voxel_kernels.py:88-105) ------------------------------------------------
+__global__ void __launch_bounds__(256)
+hash_kernel(const float4 *__restrict__ pos_m, uint32_t *__restrict__ keys, int n, GridDesc g) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 p = pos_m[i];
+    keys[i] = key_of(g, p.x, p.y, p.z);
+}
+
+// ---- __populate_voxel_begins (voxel_sph_strategy.py:98-107) + gather into cell-contiguous SoA ---------------------
+// cell_range must be zeroed before the launch: an empty cell keeps (0, 0).
+__global__ void __launch_bounds__(256)
+reorder_kernel(const uint32_t *__restrict__ skeys, const uint32_t *__restrict__ sids,
+               const float4 *__restrict__ pos_m, const float4 *__restrict__ vel_m, float4 *__restrict__ spos,
+               float4 *__restrict__ svel, int2 *__restrict__ cell_range, int n) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const uint32_t key = skeys[t];
+    const uint32_t id = sids[t];
+    if (t == 0) {
+        cell_range[key].x = 0;
+    } else {
+        const uint32_t prev = skeys[t - 1];
+        if (prev != key) {
+            cell_range[key].x = t;
+            cell_range[prev].y = t;
+        }
+    }
+    if (t == n - 1) cell_range[key].y = n;
+    spos[t] = pos_m[id];
+    svel[t] = vel_m[id];
+}
+
+// ---- host boundary converters -------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+pack_state_kernel(const T *__restrict__ pos3, const T *__restrict__ vel3, float4 *__restrict__ pos_m,
+                  float4 *__restrict__ vel_m, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    pos_m[i] = make_float4((float)pos3[3 * (size_t)i], (float)pos3[3 * (size_t)i + 1], (float)pos3[3 * (size_t)i + 2],
+                           0.f);
+    vel_m[i] = make_float4((float)vel3[3 * (size_t)i], (float)vel3[3 * (size_t)i + 1], (float)vel3[3 * (size_t)i + 2],
+                           0.f);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+unpack_state_kernel(const float4 *__restrict__ pos_m, const float4 *__restrict__ vel_m, T *__restrict__ pos3,
+                    T *__restrict__ vel3, T *__restrict__ rho, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 p = pos_m[i], v = vel_m[i];
+    if (pos3) {
+        pos3[3 * (size_t)i] = (T)p.x;
+        pos3[3 * (size_t)i + 1] = (T)p.y;
+        pos3[3 * (size_t)i + 2] = (T)p.z;
+    }
+    if (vel3) {
+        vel3[3 * (size_t)i] = (T)v.x;
+        vel3[3 * (size_t)i + 1] = (T)v.y;
+        vel3[3 * (size_t)i + 2] = (T)v.z;
+    }
+    if (rho) rho[i] = (T)p.w;
+}
+
+// sorted float4 -> id-ordered (N,3) fp64 (result_force and the recorded terms)
+__global__ void __launch_bounds__(256)
+unsort_vec3_kernel(const float4 *__restrict__ sorted, const uint32_t *__restrict__ sids, double *__restrict__ out3,
+                   int n) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const float4 f = sorted[t];
+    const size_t id = sids[t];
+    out3[3 * id] = f.x;
+    out3[3 * id + 1] = f.y;
+    out3[3 * id + 2] = f.z;
+}
+
+// sorted neighbour counts (low 7 bits of ncnt) -> id-ordered int32
+__global__ void __launch_bounds__(256)
+unsort_count_kernel(const uint8_t *__restrict__ sorted, const uint32_t *__restrict__ sids, int32_t *__restrict__ out,
+                    int n) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) out[sids[t]] = sorted[t] & 0x7f;
+}
+
+// voxel_begin as the reference stores it: first map index of the cell, -1 if empty (voxel_sph_strategy.py:92-107)
+__global__ void __launch_bounds__(256)
+voxel_begin_kernel(const int2 *__restrict__ cell_range, int32_t *__restrict__ begin, int ncells) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncells) return;
+    const int2 r = cell_range[c];
+    begin[c] = (r.y > r.x) ? r.x : -1;
+}
+
+// analize.py-style reductions: [0] non-finite count, [1] max density bits, [2] max speed bits
+__global__ void __launch_bounds__(256)
+stats_kernel(const float4 *__restrict__ pos_m, const float4 *__restrict__ vel_m, int n, uint32_t *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t bad = 0;
+    float rho = 0.f, sp = 0.f;
+    if (i < n) {
+        const float4 p = pos_m[i], v = vel_m[i];
+        const bool fin = isfinite(p.x) && isfinite(p.y) && isfinite(p.z) && isfinite(v.x) && isfinite(v.y) &&
+                         isfinite(v.z);
+        bad = fin ? 0u : 1u;
+        if (isfinite(p.w)) rho = fmaxf(p.w, 0.f);
+        if (fin) sp = sqrtf(v.x * v.x + v.y * v.y + v.z * v.z);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        bad += __shfl_xor_sync(0xffffffffu, bad, o);
+        rho = fmaxf(rho, __shfl_xor_sync(0xffffffffu, rho, o));
+        sp = fmaxf(sp, __shfl_xor_sync(0xffffffffu, sp, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (bad) atomicAdd(&out[0], bad);
+        atomicMax(&out[1], __float_as_uint(rho));
+        atomicMax(&out[2], __float_as_uint(sp));
+    }
+}
+
+}  // namespace sph

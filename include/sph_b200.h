@@ -30,7 +30,7 @@ extern "C" {
 #define SPH_MODE_BOX 0   /* config.SIM_MODE == 'BOX'  -> collision_kernel_box  (base_kernels.py:75-98)  */
 #define SPH_MODE_PIPE 1  /* config.SIM_MODE == 'PIPE' -> collision_kernel      (base_kernels.py:56-72)  */
 
-#define SPH_FLAG_RECORD_NEIGHBOUR_COUNTS 1u /* density sweep also stores min(32, #in range) per particle (parity tap) */
+#define SPH_FLAG_RECORD_NEIGHBOUR_COUNTS 1u /* accepted for compatibility: neighbour counts are always kept (1 B/particle) */
 #define SPH_FLAG_RECORD_TERMS 2u            /* force sweep also stores the pressure and viscosity terms (parity tap)  */
 #define SPH_FLAG_NO_GRAPH 4u                /* launch kernels eagerly instead of replaying a CUDA graph             */
 
@@ -114,6 +114,12 @@ int sph_compute_next_state(sph_handle_t h, const double *pos_in, const double *v
                            double *vel_out, double *density_out);
 
 int sph_sync(sph_handle_t h);
+
+/* Device-side snapshot / restore of the particle state (position, velocity, density, rng states, step counter).
+ * No reference counterpart (the reference restarts from config.start_state, sim/src/main.py:14); used for
+ * checkpoint/resume and by bench.py to keep a workload inside its first steps. */
+int sph_save_state(sph_handle_t h);
+int sph_restore_state(sph_handle_t h);
 
 /* ---- parity taps: state of the most recent step --------------------------------------------------------------- */
 int sph_get_keys(sph_handle_t h, int32_t *keys);                 /* self.voxels            voxel_sph_strategy.py:82 */
