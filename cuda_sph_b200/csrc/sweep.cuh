@@ -323,15 +323,16 @@ density_kernel(const SweepArgs a, const GridDesc g, const StepConsts c) {
             __syncwarp();
 
             // ---- rounds: 32 lanes x 2 candidates against one particle at a time ----
-            const int cnt_before = my_cnt;
             unsigned todo = pending;
             while (todo) {
                 const int i = __ffs(todo) - 1;
                 todo &= todo - 1;
                 const float4 p = sm.ppos[i];                     // broadcast
                 const float2 px2 = make_float2(p.x, p.x), py2 = make_float2(p.y, p.y), pz2 = make_float2(p.z, p.z);
+                const int self_i = __shfl_sync(FULL, self_v, i) - pbase - lane;   // == r*64 (+32) for the own slot
                 int cnt = __shfl_sync(FULL, my_cnt, i);
-                uint16_t *row = &sm.list[i * LIST_STRIDE];
+                uint16_t *wr = &sm.list[i * LIST_STRIDE + cnt];   // next free list slot of particle i
+                float part = 0.f;
 #pragma unroll
                 for (int r = 0; r < TILE / 64; ++r) {
                     if (r * 64 >= plen) break;
@@ -339,43 +340,43 @@ density_kernel(const SweepArgs a, const GridDesc g, const StepConsts c) {
                     const float2 dy = __fadd2_rn(py2, sm.ty[r * 32 + lane]);
                     const float2 dz = __fadd2_rn(pz2, sm.tz[r * 32 + lane]);
                     const float2 r2 = __ffma2_rn(dz, dz, __ffma2_rn(dy, dy, __fmul2_rn(dx, dx)));
-                    bool in0 = r2.x <= c.h2_lo, in1 = r2.y <= c.h2_lo;
-                    if ((!in0 && r2.x < c.h2_hi) || (!in1 && r2.y < c.h2_hi)) {   // rare: fp64 decides inside the band
+                    unsigned m0 = __ballot_sync(FULL, r2.x <= c.h2_lo), m1 = __ballot_sync(FULL, r2.y <= c.h2_lo);
+                    // rare (warp-uniform branch): some candidate sits inside the rounding band -> fp64 decides
+                    if (__any_sync(FULL, (r2.x > c.h2_lo && r2.x < c.h2_hi) || (r2.y > c.h2_lo && r2.y < c.h2_hi))) {
+                        bool in0 = r2.x <= c.h2_lo, in1 = r2.y <= c.h2_lo;
                         if (!in0 && r2.x < c.h2_hi)
                             in0 = in_range_exact(p.x, p.y, p.z, p.x - dx.x, p.y - dy.x, p.z - dz.x, c.r2_max);
                         if (!in1 && r2.y < c.h2_hi)
                             in1 = in_range_exact(p.x, p.y, p.z, p.x - dx.y, p.y - dy.y, p.z - dz.y, c.r2_max);
+                        m0 = __ballot_sync(FULL, in0);
+                        m1 = __ballot_sync(FULL, in1);
                     }
-                    const unsigned m0 = __ballot_sync(FULL, in0), m1 = __ballot_sync(FULL, in1);
-                    // positions in the particle's list: "first 32 hits" == position < 32
-                    const int pos0 = cnt + __popc(m0 & lt);
-                    const int pos1 = cnt + __popc(m0) + __popc(m1 & lt);
-                    if (in0 && pos0 < kMaxNeighbours) row[pos0] = (uint16_t)(pbase + r * 64 + lane);
-                    if (in1 && pos1 < kMaxNeighbours) row[pos1] = (uint16_t)(pbase + r * 64 + 32 + lane);
-                    cnt += __popc(m0) + __popc(m1);
+                    // list positions: "first 32 hits" == position < 32
+                    const int n0 = __popc(m0);
+                    const int k0 = __popc(m0 & lt), k1 = n0 + __popc(m1 & lt);
+                    const int room = kMaxNeighbours - cnt;
+                    const bool t0 = ((m0 >> lane) & 1u) && k0 < room, t1 = ((m1 >> lane) & 1u) && k1 < room;
+                    if (t0) wr[k0] = (uint16_t)(pbase + r * 64 + lane);
+                    if (t1) wr[k1] = (uint16_t)(pbase + r * 64 + 32 + lane);
+                    // poly6 terms of the accepted candidates (self excluded): (h^2 - r^2)^3
+                    const float d0 = c.h2 - r2.x, d1 = c.h2 - r2.y;
+                    const float w0 = (t0 && self_i != r * 64) ? d0 * d0 * d0 : 0.f;
+                    const float w1 = (t1 && self_i != r * 64 + 32) ? d1 * d1 * d1 : 0.f;
+                    part += w0 + w1;
+                    const int n = n0 + __popc(m1);
+                    cnt += n;
+                    wr += n;
                     if (cnt >= kMaxNeighbours) {
                         cnt = kMaxNeighbours;
                         pending &= ~(1u << i);
                         break;
                     }
                 }
-                if (lane == i) my_cnt = cnt;
-            }
-            __syncwarp();
-            // ---- lane = particle: add the poly6 terms of the entries this piece appended, in scan order ----
-            {
-                const float *fx = reinterpret_cast<const float *>(sm.tx), *fy = reinterpret_cast<const float *>(sm.ty),
-                            *fz = reinterpret_cast<const float *>(sm.tz);
-                const uint16_t *row = &sm.list[lane * LIST_STRIDE];
-                for (int e = cnt_before; e < my_cnt; ++e) {
-                    const int v = row[e];
-                    const int q = v - pbase;
-                    const int slot = ((q >> 6) * 32 + (q & 31)) * 2 + ((q >> 5) & 1);
-                    const float ddx = pi.x + fx[slot], ddy = pi.y + fy[slot], ddz = pi.z + fz[slot];
-                    const float r2 = fmaf(ddz, ddz, fmaf(ddy, ddy, ddx * ddx));
-                    const float d = c.h2 - r2;
-                    const float w = (v != self_v) ? d * d * d : 0.f;
-                    my_rho += w;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(FULL, part, o);
+                if (lane == i) {
+                    my_cnt = cnt;
+                    my_rho += part;
                 }
             }
         }

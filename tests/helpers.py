@@ -38,13 +38,19 @@ def max_rel(a, b):
     return float(np.max(np.abs(a[fin] - b[fin]) / np.maximum(np.abs(b[fin]), 1e-300)))
 
 
-def vec_rel(a, b):
-    """per-particle ||a-b|| / ||b||  (rows with non-finite reference must match exactly), returns the max."""
+def vec_rel(a, b, floor=None):
+    """max over particles of ||a_i - b_i|| / max(||b_i||, floor_i).  Rows whose reference is non-finite must be
+    non-finite in the same places.  `floor` (per particle) is used for the pressure / viscosity TERMS only: they act
+    through the net force, so their error is judged against max(|term|, |force|) -- a viscosity component that is a
+    cancelling sum of 1e4-sized pair terms next to two components clamped to 1 is not a 1e-4-relative quantity."""
     a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
     fin = np.isfinite(b).all(axis=1)
-    assert same(a[~fin], b[~fin]) or np.array_equal(np.isfinite(a[~fin]), np.isfinite(b[~fin]))
+    assert np.array_equal(np.isfinite(a[~fin]), np.isfinite(b[~fin])), "non-finite patterns differ"
     if not fin.any():
         return 0.0
     num = np.linalg.norm(a[fin] - b[fin], axis=1)
     den = np.maximum(np.linalg.norm(b[fin], axis=1), 1e-300)
+    if floor is not None:
+        fl = np.asarray(floor, np.float64)[fin]
+        den = np.maximum(den, np.where(np.isfinite(fl), fl, 0.0))
     return float(np.max(num / den))

@@ -39,8 +39,9 @@ def _check_against(s, ref, *, rho=RHO_RTOL, vec=VEC_RTOL):
     assert np.array_equal(s.neighbour_counts(), ref["neigh_count"])
     assert max_rel(out.density, ref["density"]) <= rho
     pr, vi = s.terms()
-    assert vec_rel(pr, ref["pressure"]) <= vec
-    assert vec_rel(vi, ref["viscosity"]) <= vec
+    fnorm = np.linalg.norm(ref["force"], axis=1)
+    assert vec_rel(pr, ref["pressure"], floor=fnorm) <= vec
+    assert vec_rel(vi, ref["viscosity"], floor=fnorm) <= vec
     assert vec_rel(s.result_force, ref["force"]) <= vec
     assert vec_rel(out.velocity, ref["vel_out"]) <= vec
     assert vec_rel(out.position, ref["pos_out"]) <= vec
