@@ -372,6 +372,7 @@ def main():
     ap.add_argument("--workload", default=None, choices=[None, "dam1m", "box32m", "pipe4m"])
     ap.add_argument("--particles", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-single", action="store_true", help="multi-GPU: skip the 1-GPU run of the same workload")
     ap.add_argument("--window", type=int, default=WINDOW,
                     help="restore the start state every WINDOW steps (0 = never; see module docstring)")
     args = ap.parse_args()

@@ -9,7 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsph_b200.so")
 
 MODE_BOX, MODE_PIPE = 0, 1
-FLAG_RECORD_NEIGHBOUR_COUNTS, FLAG_RECORD_TERMS, FLAG_NO_GRAPH = 1, 2, 4
+FLAG_RECORD_NEIGHBOUR_COUNTS, FLAG_RECORD_TERMS, FLAG_NO_GRAPH, FLAG_SLAB = 1, 2, 4, 8
 
 
 class SphParams(C.Structure):
@@ -52,6 +52,8 @@ EXPORTS = {
     "sph_sync": (C.c_int, [_H]),
     "sph_save_state": (C.c_int, [_H]),
     "sph_restore_state": (C.c_int, [_H]),
+    "sph_slab_configure": (C.c_int, [_H, C.c_int32, C.c_int32, C.c_int64]),
+    "sph_slab_step": (C.c_int, [_H, C.c_int32, C.c_int32]),
     "sph_get_keys": (C.c_int, [_H, _P]),
     "sph_get_sorted_ids": (C.c_int, [_H, _P]),
     "sph_get_sorted_keys": (C.c_int, [_H, _P]),

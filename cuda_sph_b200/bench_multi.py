@@ -1,0 +1,128 @@
+"""Multi-GPU arm of bench.py: strong scaling of one box workload over x-slabs (one rank per GPU, NCCL).
+
+value = N_global x steps / (sum over windows of the max-over-ranks device time).  Every window starts from the same
+start state (see bench.py "Window"): each rank snapshots its slab after loading and restores it between windows,
+outside the timed events."""
+from __future__ import annotations
+
+import json
+import time
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def run(args, rank, world, local_rank):
+    import bench
+    from .slab import GpuSlabRunner, equal_count_bounds
+    from .strategy import B200SPHStrategy, SphConstants
+
+    name = args.workload or "box32m"
+    params, st, mode, desc = bench.make_workload(name, args.particles)
+    n = int(params.particle_count)
+    voxel_x = float(params.voxel_size[0])
+    n_cols = int(np.ceil(params.space_size[0] / voxel_x))
+    cols = np.clip((st.position[:, 0] / voxel_x).astype(np.int64), 0, n_cols - 1)
+    hist = np.bincount(cols, minlength=n_cols)
+    bounds = equal_count_bounds(hist, world)
+    own = int(hist[bounds[rank]:bounds[rank + 1]].sum())
+    capacity = int(1.35 * max(own, n // world)) + 6 * int(hist.max()) + 4096
+    window = args.window
+    K, W = args.steps, max(args.warmup, 3)
+    dev = torch.device("cuda", local_rank)
+
+    # ---- single-GPU reference point on the same workload (rank 0 only, short) ----
+    single = None
+    if rank == 0 and not args.no_single:
+        s1 = B200SPHStrategy(params, SphConstants(mode=mode), device=local_rank)
+        s1.upload(st)
+        s1.save_state()
+        s1.step(2)
+        s1.synchronize()
+        tot = 0.0
+        for _ in range(2):
+            s1.restore_state()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s1.synchronize()
+            t0 = time.perf_counter()
+            s1.step(window or 4)
+            s1.synchronize()
+            tot += time.perf_counter() - t0
+        single = n * 2 * (window or 4) / tot
+        s1.close()
+        del s1
+        torch.cuda.empty_cache()
+    dist.barrier()
+
+    run_ = GpuSlabRunner(params, SphConstants(mode=mode), capacity=capacity, bounds=bounds, device=local_rank)
+    run_.load_global(st.position, st.velocity)
+    snap = (run_.P[:run_.n_own].clone(), run_.V[:run_.n_own].clone(), run_.G[:run_.n_own].clone(), run_.n_own)
+
+    def restore():
+        k = snap[3]
+        run_.P[:k], run_.V[:k], run_.G[:k] = snap[0], snap[1], snap[2]
+        run_.n_own = run_.n_local = k
+
+    def timed_steps(k):
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        run_.step(k)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    done = 0
+    while done < W:
+        g = min(window or W, W - done)
+        if window:
+            restore()
+        run_.step(g)
+        done += g
+    sampler = bench.ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = run_.launch_count()
+    ms_total, done = 0.0, 0
+    t_wall0 = time.perf_counter()
+    while done < K:
+        g = min(window or K, K - done)
+        if window:
+            restore()
+        ms_total += timed_steps(g)
+        done += g
+    t_wall = time.perf_counter() - t_wall0
+    launches = torch.tensor([run_.launch_count() - launches0], device=dev)
+    dist.all_reduce(launches)
+    cnt = run_.count_global()
+    stats = torch.tensor([run_.stats["halo_sent"], run_.stats["migrated"], run_.n_own], device=dev, dtype=torch.float64)
+    allstats = [torch.empty_like(stats) for _ in range(world)]
+    dist.all_gather(allstats, stats)
+    clocks = sampler.stop() if rank == 0 else None
+    assert cnt == n, f"particles lost: {cnt} != {n}"
+    if rank == 0:
+        value = n * K / (ms_total * 1e-3)
+        steps_total = max(run_.stats["steps"], 1)
+        line = {"metric": bench.METRIC, "value": value, "unit": bench.UNIT, "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": {"workload": desc, "name": name, "particles": n,
+                           "parallelism": f"x-slabs x{world}, 2-column ghost halos + migration (all_to_all over NCCL)",
+                           "slab_bounds": bounds, "capacity_per_rank": capacity,
+                           "window": f"state restored to the start state every {window} steps (untimed)"
+                           if window else "none", "l2": "working set per GPU larger than L2: no flush",
+                           "timing": "CUDA events per window, max over ranks, barrier + synchronize on both sides"},
+                "wall_s_timed_region": t_wall, "clocks": clocks, "gpu_launches": int(launches.item()),
+                "e2e": None, "roofline": None, "cpu_baseline": None,
+                "value_1gpu_same_workload": single,
+                "halo_particles_per_step_per_rank": [float(s[0]) / steps_total for s in allstats],
+                "migrated_per_step_per_rank": [float(s[1]) / steps_total for s in allstats],
+                "owned_per_rank": [int(s[2]) for s in allstats]}
+        print(json.dumps(line), flush=True)
+    run_.close()
+    dist.barrier()
+    dist.destroy_process_group()

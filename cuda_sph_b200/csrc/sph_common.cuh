@@ -17,6 +17,9 @@ struct GridDesc {
     int32_t wn, hn;      // neighbour-cell strides (trunc dims; == wk, hk when space is a multiple of voxel)
     int32_t tx, ty, tz;  // trunc dims: a neighbour cell must satisfy 0 <= c_d < t_d
     int32_t ncells;      // table size; key == ncells is the dead cell
+    // x-slab decomposition (multi-GPU).  Single GPU: strict_x = 0, own_lo = INT_MIN/2, own_hi = INT_MAX/2.
+    int32_t strict_x;    // 1: a particle whose x column falls outside the local table [xoff, xoff + wk) is dead
+    int32_t own_lo, own_hi;  // owned x columns [own_lo, own_hi); density is also computed one column beyond
 };
 
 struct StepConsts {
@@ -52,6 +55,7 @@ __device__ __forceinline__ bool cell_of(const GridDesc &g, float x, float y, flo
 __device__ __forceinline__ uint32_t key_of(const GridDesc &g, float x, float y, float z) {
     int vx, vy, vz;
     if (!cell_of(g, x, y, z, vx, vy, vz)) return (uint32_t)g.ncells;
+    if (g.strict_x && (vx < g.xoff || vx >= g.xoff + g.wk)) return (uint32_t)g.ncells;
     const long long k = (long long)vx - g.xoff + (long long)vy * g.wk + (long long)vz * g.wk * g.hk;
     return (k >= 0 && k < g.ncells) ? (uint32_t)k : (uint32_t)g.ncells;
 }

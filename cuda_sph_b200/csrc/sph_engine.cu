@@ -3,6 +3,7 @@
 // Step pipeline (device resident, replayed as a CUDA graph):
 //   hash_kernel -> [rs_hist, rs_scan, rs_scatter] x passes -> memset(cell_range) -> reorder_kernel
 //   -> density_kernel -> force_kernel (pressure + viscosity + integrate + collide, scatter to master)
+#include <climits>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -55,6 +56,12 @@ struct SphEngine {
     double *pipe_d = nullptr;
     int pipe_rows = 0;
     uint64_t *rng = nullptr;
+    int64_t rng_count = 0;
+    // x-slab mode (multi-GPU)
+    bool slab = false;
+    int32_t *gid = nullptr;       // global particle id per local index
+    int32_t slab_lo = 0, slab_hi = 0;
+    int64_t cell_capacity = 0;    // entries allocated in cell_range
     // host-boundary staging (fp64 / fp32 (N,3) + rho), grown lazily
     void *stage = nullptr;
     size_t stage_bytes = 0;
@@ -171,6 +178,24 @@ int sph_create(const SphParams *params, int device, sph_handle_t *out) {
     e->grid.ty = e->trunc_dims[1];
     e->grid.tz = e->trunc_dims[2];
     e->grid.ncells = (int32_t)ncells;
+    e->grid.strict_x = 0;
+    e->grid.own_lo = INT32_MIN / 2;
+    e->grid.own_hi = INT32_MAX / 2;
+    e->slab = (params->flags & SPH_FLAG_SLAB) != 0;
+    long long table_cells = ncells;
+    if (e->slab) {
+        for (int d = 0; d < 3; ++d)
+            if (e->ceil_dims[d] != e->trunc_dims[d]) {
+                delete e;
+                return fail("x-slab mode needs space_size to be a multiple of voxel_size");
+            }
+        table_cells = (long long)(e->ceil_dims[0] + 4) * e->ceil_dims[1] * e->ceil_dims[2];
+        if (table_cells >= (1LL << 31) - 2) {
+            delete e;
+            return fail("cell table too large for int32 keys");
+        }
+    }
+    e->cell_capacity = table_cells + 1;
 
     // constants (config.py:24-29)
     const double h = params->h;
@@ -201,7 +226,7 @@ int sph_create(const SphParams *params, int device, sph_handle_t *out) {
 
     // radix passes over the bits of [0, ncells] (ncells itself = dead cell)
     int bits = 1;
-    while ((1LL << bits) <= ncells) ++bits;
+    while ((1LL << bits) <= table_cells) ++bits;
     e->key_bits = bits;
     e->passes = (bits + 7) / 8;
     for (int i = 0; i < e->passes; ++i) e->pass_bits[i] = bits / e->passes + (i < bits % e->passes ? 1 : 0);
@@ -229,7 +254,8 @@ int sph_create(const SphParams *params, int device, sph_handle_t *out) {
     ALLOC(e->vb, n);
     ALLOC(e->block_hist, (size_t)RS_RADIX * e->ntiles);
     ALLOC(e->digit_total, RS_RADIX);
-    ALLOC(e->cell_range, ncells + 1);
+    ALLOC(e->cell_range, e->cell_capacity);
+    if (e->slab) ALLOC(e->gid, n);
     ALLOC(e->stats_d, 4);
     ALLOC(e->nlist, (size_t)n * 32);
     ALLOC(e->ncnt, n);
@@ -237,7 +263,8 @@ int sph_create(const SphParams *params, int device, sph_handle_t *out) {
         ALLOC(e->spress, n);
         ALLOC(e->svisc, n);
     }
-    if (params->mode == SPH_MODE_PIPE) {
+    if (params->mode == SPH_MODE_PIPE && !e->slab) {   // slab mode: sph_slab_configure sizes it by the global count
+        e->rng_count = n;
         ALLOC(e->rng, 2 * (size_t)n);
         std::vector<uint64_t> st;
         init_rng_host(st, n, params->rng_seed);
@@ -257,7 +284,7 @@ int sph_create(const SphParams *params, int device, sph_handle_t *out) {
     cudaMemset(e->sforce, 0, sizeof(float4) * (size_t)n);
     cudaMemset(e->srho, 0, sizeof(float) * (size_t)n);
     cudaMemset(e->keys, 0, sizeof(uint32_t) * (size_t)n);
-    cudaMemset(e->cell_range, 0, sizeof(int2) * (size_t)(ncells + 1));
+    cudaMemset(e->cell_range, 0, sizeof(int2) * (size_t)e->cell_capacity);
     if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) {
         sph_destroy(e);
         return fail("cudaStreamCreate failed");
@@ -280,7 +307,7 @@ int sph_destroy(sph_handle_t e) {
     invalidate_graph(e);
     void *ptrs[] = {e->pos_m, e->vel_m, e->spos, e->svel, e->sforce, e->spress, e->svisc, e->srho, e->nlist, e->ncnt,
                     e->keys, e->ka, e->va, e->kb, e->vb, e->block_hist, e->digit_total, e->cell_range, e->pipe_d,
-                    e->rng, e->stage, e->stats_d, e->snap_pos, e->snap_vel, e->snap_rng};
+                    e->rng, e->gid, e->stage, e->stats_d, e->snap_pos, e->snap_vel, e->snap_rng};
     for (void *q : ptrs)
         if (q) cudaFree(q);
     for (auto &ev : e->ev)
@@ -357,10 +384,10 @@ int sph_download(sph_handle_t e, double *p, double *v, double *r) { return downl
 int sph_download_f32(sph_handle_t e, float *p, float *v, float *r) { return download_impl<float>(e, p, v, r); }
 
 // Enqueue one step on e->stream.  If evs != nullptr, records stage boundaries into e->ev[0..5].
-static int enqueue_step(SphEngine *e, bool timed) {
-    const int n = e->n;
+static int enqueue_step(SphEngine *e, bool timed, int n, int n_own) {
     cudaStream_t s = e->stream;
     const int g256 = (n + 255) / 256;
+    const int ntiles = (n + RS_TILE - 1) / RS_TILE;
     if (timed) cudaEventRecord(e->ev[0], s);
     hash_kernel<<<g256, 256, 0, s>>>(e->pos_m, e->keys, n, e->grid);
     if (timed) cudaEventRecord(e->ev[1], s);
@@ -372,10 +399,10 @@ static int enqueue_step(SphEngine *e, bool timed) {
             uint32_t *kout = (p % 2 == 0) ? e->ka : e->kb;
             uint32_t *vout = (p % 2 == 0) ? e->va : e->vb;
             const uint32_t mask = (1u << e->pass_bits[p]) - 1u;
-            rs_hist<<<e->ntiles, RS_THREADS, 0, s>>>(kin, n, shift, mask, e->block_hist, e->ntiles);
-            rs_scan<<<RS_RADIX, RS_THREADS, 0, s>>>(e->block_hist, e->ntiles, e->digit_total);
-            rs_scatter<<<e->ntiles, RS_THREADS, 0, s>>>(kin, vin, kout, vout, n, shift, mask, e->block_hist,
-                                                        e->ntiles, e->digit_total);
+            rs_hist<<<ntiles, RS_THREADS, 0, s>>>(kin, n, shift, mask, e->block_hist, ntiles);
+            rs_scan<<<RS_RADIX, RS_THREADS, 0, s>>>(e->block_hist, ntiles, e->digit_total);
+            rs_scatter<<<ntiles, RS_THREADS, 0, s>>>(kin, vin, kout, vout, n, shift, mask, e->block_hist, ntiles,
+                                                     e->digit_total);
             kin = kout;
             vin = vout;
             shift += e->pass_bits[p];
@@ -383,13 +410,20 @@ static int enqueue_step(SphEngine *e, bool timed) {
     }
     if (timed) cudaEventRecord(e->ev[2], s);
     cudaMemsetAsync(e->cell_range, 0, sizeof(int2) * ((size_t)e->grid.ncells + 1), s);
-    reorder_kernel<<<g256, 256, 0, s>>>(e->skeys, e->sids, e->pos_m, e->vel_m, e->spos, e->svel, e->cell_range, n);
+    const uint32_t *sids = e->sids;
+    if (e->slab) {   // in-cell order by GLOBAL id (the local index order is arrival order on a slab)
+        uint32_t *fixed = (e->sids == e->va) ? e->vb : e->va;
+        cell_range_kernel<<<g256, 256, 0, s>>>(e->skeys, e->cell_range, n);
+        fix_order_kernel<<<g256, 256, 0, s>>>(e->skeys, e->sids, fixed, e->gid, e->cell_range, n);
+        sids = fixed;
+    }
+    reorder_kernel<<<g256, 256, 0, s>>>(e->skeys, sids, e->pos_m, e->vel_m, e->spos, e->svel, e->cell_range, n);
     if (timed) cudaEventRecord(e->ev[3], s);
     SweepArgs sa{};
     sa.spos = e->spos;
     sa.svel = e->svel;
     sa.skeys = e->skeys;
-    sa.sids = e->sids;
+    sa.sids = sids;
     sa.cell_range = e->cell_range;
     sa.srho = e->srho;
     sa.nlist = e->nlist;
@@ -401,7 +435,9 @@ static int enqueue_step(SphEngine *e, bool timed) {
     sa.svisc = e->svisc;
     sa.pipe = e->pipe_d;
     sa.rng = e->rng;
+    sa.gid = e->slab ? e->gid : nullptr;
     sa.n = n;
+    sa.n_own = n_own;
     const int gsw = (n + SW_THREADS - 1) / SW_THREADS;
     density_kernel<<<gsw, SW_THREADS, 0, s>>>(sa, e->grid, e->consts);
     if (timed) cudaEventRecord(e->ev[4], s);
@@ -416,6 +452,7 @@ static int enqueue_step(SphEngine *e, bool timed) {
 
 static int check_ready(SphEngine *e) {
     if (!e) return fail("null handle");
+    if (e->slab) return fail("this handle is in x-slab mode: use sph_slab_step");
     if (!e->has_state) return fail("no particle state: call sph_upload first");
     if (e->p.mode == SPH_MODE_PIPE && !e->pipe_d) return fail("PIPE mode needs sph_set_pipe before stepping");
     return 0;
@@ -427,11 +464,11 @@ int sph_step(sph_handle_t e, int32_t n_steps) {
     CK(cudaSetDevice(e->device));
     if (e->p.flags & SPH_FLAG_NO_GRAPH) {
         for (int i = 0; i < n_steps; ++i)
-            if (enqueue_step(e, false)) return 1;
+            if (enqueue_step(e, false, e->n, e->n)) return 1;
     } else {
         if (!e->graph_valid) {
             CK(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
-            const int rc = enqueue_step(e, false);
+            const int rc = enqueue_step(e, false, e->n, e->n);
             cudaGraph_t g = nullptr;
             cudaError_t ce = cudaStreamEndCapture(e->stream, &g);
             if (rc) return 1;
@@ -453,7 +490,7 @@ int sph_step_timed(sph_handle_t e, int32_t n_steps, SphTimings *t) {
     CK(cudaSetDevice(e->device));
     memset(t, 0, sizeof(*t));
     for (int i = 0; i < n_steps; ++i) {
-        if (enqueue_step(e, true)) return 1;
+        if (enqueue_step(e, true, e->n, e->n)) return 1;
         CK(cudaEventSynchronize(e->ev[5]));
         float ms[5];
         for (int k = 0; k < 5; ++k) CK(cudaEventElapsedTime(&ms[k], e->ev[k], e->ev[k + 1]));
@@ -506,6 +543,49 @@ int sph_restore_state(sph_handle_t e) {
     if (e->rng)
         CK(cudaMemcpyAsync(e->rng, e->snap_rng, 2 * sizeof(uint64_t) * n, cudaMemcpyDeviceToDevice, e->stream));
     e->steps_done = e->snap_steps;
+    return 0;
+}
+
+int sph_slab_configure(sph_handle_t e, int32_t x_lo, int32_t x_hi, int64_t n_global) {
+    if (!e) return fail("null handle");
+    if (!e->slab) return fail("create the engine with SPH_FLAG_SLAB");
+    if (x_lo < 0 || x_hi > e->ceil_dims[0] || x_lo >= x_hi) return fail("bad slab column range");
+    CK(cudaSetDevice(e->device));
+    CK(cudaStreamSynchronize(e->stream));
+    e->slab_lo = x_lo;
+    e->slab_hi = x_hi;
+    GridDesc &g = e->grid;
+    g.xoff = x_lo - 2;                       // two ghost columns on each side
+    g.wk = (x_hi - x_lo) + 4;
+    g.wn = g.wk;
+    g.ncells = g.wk * e->ceil_dims[1] * e->ceil_dims[2];
+    g.strict_x = 1;
+    g.own_lo = x_lo;
+    g.own_hi = x_hi;
+    if (e->p.mode == SPH_MODE_PIPE && e->rng_count != n_global) {
+        if (e->rng) cudaFree(e->rng);
+        e->rng = nullptr;
+        CK(cudaMalloc((void **)&e->rng, 2 * sizeof(uint64_t) * (size_t)n_global));
+        std::vector<uint64_t> st;
+        init_rng_host(st, n_global, e->p.rng_seed);
+        CK(cudaMemcpy(e->rng, st.data(), st.size() * sizeof(uint64_t), cudaMemcpyHostToDevice));
+        e->rng_count = n_global;
+    }
+    e->has_state = true;
+    return 0;
+}
+
+int sph_slab_step(sph_handle_t e, int32_t n_own, int32_t n_local) {
+    if (!e) return fail("null handle");
+    if (!e->slab) return fail("create the engine with SPH_FLAG_SLAB");
+    if (e->slab_hi <= e->slab_lo) return fail("call sph_slab_configure first");
+    if (n_own < 0 || n_local < n_own || n_local > e->n) return fail("bad particle counts (capacity exceeded?)");
+    if (e->p.mode == SPH_MODE_PIPE && !e->pipe_d) return fail("PIPE mode needs sph_set_pipe before stepping");
+    if (n_local == 0) return 0;
+    CK(cudaSetDevice(e->device));
+    if (enqueue_step(e, false, n_local, n_own)) return 1;
+    e->steps_done += 1;
+    e->launches += e->launches_per_step + 2;
     return 0;
 }
 
@@ -624,6 +704,8 @@ int sph_device_ptr(sph_handle_t e, int32_t which, void **ptr, int64_t *n_element
         case 1: q = e->vel_m; break;
         case 2: q = e->sids; break;
         case 3: q = e->spos; break;
+        case 4: q = e->gid; break;
+        case 5: q = e->rng; break;
         default: return fail("unknown buffer id");
     }
     *ptr = q;

@@ -44,6 +44,41 @@ reorder_kernel(const uint32_t *__restrict__ skeys, const uint32_t *__restrict__ 
     svel[t] = vel_m[id];
 }
 
+// ---- x-slab mode only: make the order inside every cell ascending in GLOBAL particle id ------------------------------
+// On one GPU the local index is the particle id, so the stable sort already yields the reference's (voxel_id,
+// particle_id) order.  On a slab the local arrays hold owned particles in arrival order followed by ghosts, so the
+// in-cell order is repaired here: rank = number of particles of the same cell with a smaller global id.
+__global__ void __launch_bounds__(256)
+cell_range_kernel(const uint32_t *__restrict__ skeys, int2 *__restrict__ cell_range, int n) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const uint32_t key = skeys[t];
+    if (t == 0) {
+        cell_range[key].x = 0;
+    } else {
+        const uint32_t prev = skeys[t - 1];
+        if (prev != key) {
+            cell_range[key].x = t;
+            cell_range[prev].y = t;
+        }
+    }
+    if (t == n - 1) cell_range[key].y = n;
+}
+
+__global__ void __launch_bounds__(256)
+fix_order_kernel(const uint32_t *__restrict__ skeys, const uint32_t *__restrict__ sids_in,
+                 uint32_t *__restrict__ sids_out, const int32_t *__restrict__ gid,
+                 const int2 *__restrict__ cell_range, int n) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const int2 r = cell_range[skeys[t]];
+    const uint32_t me = sids_in[t];
+    const int32_t g = gid[me];
+    int rank = 0;
+    for (int u = r.x; u < r.y; ++u) rank += (gid[sids_in[u]] < g) ? 1 : 0;
+    sids_out[r.x + rank] = me;
+}
+
 // ---- host boundary converters -------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(256)

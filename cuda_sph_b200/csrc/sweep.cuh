@@ -47,7 +47,9 @@ struct SweepArgs {
     float4 *pos_m, *vel_m, *sforce, *spress, *svisc;  // force sweep outputs
     const double *pipe;
     uint64_t *rng;
-    int n;
+    const int32_t *gid;   // x-slab mode: global particle id per local index (rng states are indexed by it); else null
+    int n;                // local particles (owned + ghosts)
+    int n_own;            // local indices < n_own are owned: only those are integrated and written back
 };
 
 // Exact fp64 predicate sqrt(dx^2+dy^2+dz^2) <= INF_R on the promoted fp32 coordinates, no FMA contraction (the
@@ -129,9 +131,10 @@ __device__ __forceinline__ void finish_particle(const SweepArgs &a, const StepCo
         x[d] += v[d] * c.dt;
     }
     const uint32_t id = a.sids[t];
+    if ((int)id >= a.n_own) return;   // ghost particle of an x-slab: its owner integrates it
     if (c.mode == 1) {
         PipeView pv{a.pipe, c.pipe_rows};
-        collide_pipe(pv, x, v, a.rng + 2 * (size_t)id);
+        collide_pipe(pv, x, v, a.rng + 2 * (size_t)(a.gid ? (uint32_t)a.gid[id] : id));
     } else {
         collide_box(x, v, c);
     }
@@ -213,12 +216,15 @@ struct ForceSmem {
 };
 
 // Work-item header shared by both sweeps: decode the chunk, build the segment table.  Returns T (virtual list length).
-__device__ __forceinline__ int build_segments(const SweepArgs &a, const GridDesc &g, SegTable &sm, int lane,
-                                              uint32_t ckey, int &cx, int &cy, int &cz) {
+__device__ __forceinline__ void decode_cell(const GridDesc &g, uint32_t ckey, int &cx, int &cy, int &cz) {
     cz = (int)(ckey / (uint32_t)(g.wk * g.hk));
     const int rem = (int)(ckey - (uint32_t)cz * (uint32_t)(g.wk * g.hk));
     cy = rem / g.wk;
     cx = rem - cy * g.wk + g.xoff;
+}
+
+__device__ __forceinline__ int build_segments(const SweepArgs &a, const GridDesc &g, SegTable &sm, int lane, int cx,
+                                              int cy, int cz) {
     int2 r = make_int2(0, 0);
     if (lane < 27) {   // lane -> (dx, dy, dz) with dx outermost, dz innermost (voxel_kernels.py:46-48)
         const int x = cx + lane / 9 - 1, y = cy + (lane / 3) % 3 - 1, z = cz + lane % 3 - 1;
@@ -282,7 +288,9 @@ density_kernel(const SweepArgs a, const GridDesc g, const StepConsts c) {
         const int tt = cs + lane;
         const bool mine = lane < m;
         int cx, cy, cz;
-        const int T = build_segments(a, g, sm.seg, lane, ckey, cx, cy, cz);
+        decode_cell(g, ckey, cx, cy, cz);
+        if (cx < g.own_lo - 1 || cx > g.own_hi) continue;   // x-slab: outer ghost column, nobody needs its density
+        const int T = build_segments(a, g, sm.seg, lane, cx, cy, cz);
 
         float4 pi = make_float4(0.f, 0.f, 0.f, 0.f);
         bool walk = false;
@@ -442,7 +450,9 @@ force_kernel(const SweepArgs a, const GridDesc g, const StepConsts c) {
         const int tt = cs + lane;
         const bool mine = lane < m;
         int cx, cy, cz;
-        const int T = build_segments(a, g, sm.seg, lane, ckey, cx, cy, cz);
+        decode_cell(g, ckey, cx, cy, cz);
+        if (cx < g.own_lo || cx >= g.own_hi) continue;      // x-slab: ghost cell, its owner computes the forces
+        const int T = build_segments(a, g, sm.seg, lane, cx, cy, cz);
 
         float4 pi = make_float4(0.f, 0.f, 0.f, 0.f), vi = pi;
         float rho_i = 0.f, a_i = 0.f;

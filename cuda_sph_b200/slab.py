@@ -1,0 +1,297 @@
+"""x-slab domain decomposition for multi-GPU runs (one process per GPU, torch.distributed).
+
+No reference counterpart -- the reference is single-GPU.  Interactions reach one cell
+(voxel_size >= INF_R), so rank g owns the cell columns [X_g, X_{g+1}) and needs, every step,
+
+  1. halo:      copies of the particles in the two columns on either side of its slab.  Two columns, not one,
+                because the density of a first-column ghost is recomputed locally and that needs the ghost's own
+                27 cells (saves the second exchange of the step, the one for rho);
+  2. local step (sph_slab_step): hash / sort / in-cell order by GLOBAL id / density / forces on owned + ghosts,
+                integrating owned particles only;
+  3. migration: owned particles whose new column belongs to another rank move there (any rank: the reference's
+                physics produces speeds of 1e3+ cells per step; the pipe outlet -> inlet recycle is a last -> first
+                migration), with their xoroshiro state in PIPE mode.
+
+Everything that crosses ranks is one variable-size all_to_all_single of packed byte rows (plus one for the counts).
+The partition / packing / routing logic in `SlabRunner` is device-agnostic: tests/test_slab_gloo.py drives it on CPU
+tensors over gloo with the fp64 oracle as the local step and demands bitwise equality with the single-domain oracle;
+`GpuSlabRunner` binds the same logic to the device buffers of libsph_b200.so (zero copy) over NCCL.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+HALO = 2  # ghost columns per side
+
+
+def equal_count_bounds(col_hist: np.ndarray, world: int, min_width: int = HALO) -> List[int]:
+    """Column boundaries X_0 = 0 < X_1 < ... < X_world = W with (nearly) equal particle counts per slab
+    (SURVEY.md section 7 'load balance').  Every slab is at least `min_width` columns wide so that a two-column halo
+    only ever comes from the adjacent ranks."""
+    w = int(len(col_hist))
+    if w < world * min_width:
+        raise ValueError(f"{w} cell columns cannot be split into {world} slabs of >= {min_width} columns")
+    cum = np.concatenate([[0], np.cumsum(col_hist, dtype=np.int64)])
+    total = int(cum[-1])
+    bounds = [0]
+    for g in range(1, world):
+        target = total * g / world
+        x = int(np.searchsorted(cum, target, side="left"))
+        lo = bounds[-1] + min_width
+        hi = w - (world - g) * min_width
+        bounds.append(min(max(x, lo), hi))
+    bounds.append(w)
+    return bounds
+
+
+class SlabRunner:
+    """Device-agnostic slab logic.  Sub-classes provide the storage tensors and the local step.
+
+    Storage (rows = local particle slots, capacity `cap`):
+        P [cap, 4]  x, y, z, density      V [cap, 4]  vx, vy, vz, 0      G [cap] int32 global particle id
+        R [n_global, 2] int64 xoroshiro states indexed by global id (PIPE mode) or None
+    Owned particles live in rows [0, n_own); ghosts of the current step in [n_own, n_local).
+    """
+
+    def __init__(self, n_cols: int, voxel_x: float, bounds: Sequence[int], group=None):
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.n_cols = int(n_cols)
+        self.voxel_x = float(voxel_x)
+        self.bounds = [int(b) for b in bounds]
+        assert len(self.bounds) == self.world + 1 and self.bounds[0] == 0 and self.bounds[-1] == self.n_cols
+        for g in range(self.world):
+            assert self.bounds[g + 1] - self.bounds[g] >= HALO, "slab narrower than the halo"
+        self.lo, self.hi = self.bounds[self.rank], self.bounds[self.rank + 1]
+        self.n_own = 0
+        self.n_local = 0
+        self.P = self.V = self.G = self.R = None
+        self.stats = {"halo_sent": 0, "migrated": 0, "steps": 0}
+
+    # ------------------------------------------------------------------ to be provided by the backend
+    def _local_step(self, n_own: int, n_local: int) -> None:
+        raise NotImplementedError
+
+    # ------------------------------------------------------------------ partition helpers
+    def columns(self, x: torch.Tensor) -> torch.Tensor:
+        """Cell column of a position: int32(x / voxel) with fp64 division and C truncation, as the hash kernel does
+        (voxel_kernels.py:9-12).  Non-finite -> -1."""
+        q = x.to(torch.float64) / self.voxel_x
+        fin = torch.isfinite(q) & (q.abs() < 2147483648.0)
+        col = torch.where(fin, q, torch.full_like(q, -1.0)).to(torch.int64)
+        return torch.where(fin, col, torch.full_like(col, -1))
+
+    def owner_of(self, col: torch.Tensor) -> torch.Tensor:
+        """Rank owning a column (columns outside [0, W) are clamped: such particles are dead on their owner)."""
+        b = torch.tensor(self.bounds[1:-1], dtype=torch.int64, device=col.device)
+        return torch.bucketize(col.clamp(0, self.n_cols - 1), b, right=True)
+
+    # ------------------------------------------------------------------ packed variable-size all-to-all
+    def _exchange(self, rows: torch.Tensor, dest: torch.Tensor) -> torch.Tensor:
+        """rows: [k, B] uint8, dest: [k] rank per row.  Returns the rows received (grouped by source rank)."""
+        if self.world == 1:
+            return rows[:0]
+        order = torch.argsort(dest, stable=True)
+        rows = rows[order].contiguous()
+        send = torch.bincount(dest, minlength=self.world).to(torch.int64)
+        recv = torch.empty_like(send)
+        dist.all_to_all_single(recv, send, group=self.group)
+        send_l, recv_l = send.tolist(), recv.tolist()           # host sync: sizes of the payload exchange
+        out = torch.empty((sum(recv_l), rows.shape[1]), dtype=torch.uint8, device=rows.device)
+        dist.all_to_all_single(out, rows, output_split_sizes=recv_l, input_split_sizes=send_l, group=self.group)
+        return out
+
+    def _pack(self, idx: torch.Tensor, with_rng: bool) -> torch.Tensor:
+        parts = [self.P[idx].view(torch.uint8).reshape(len(idx), -1), self.V[idx].view(torch.uint8).reshape(len(idx), -1),
+                 self.G[idx].view(torch.uint8).reshape(len(idx), -1)]
+        if with_rng and self.R is not None:
+            parts.append(self.R[self.G[idx].long()].view(torch.uint8).reshape(len(idx), -1))
+        return torch.cat(parts, dim=1)
+
+    def _unpack(self, rows: torch.Tensor, at: int, with_rng: bool) -> int:
+        k = rows.shape[0]
+        if k == 0:
+            return 0
+        if at + k > self.P.shape[0]:
+            raise RuntimeError(f"slab capacity exceeded on rank {self.rank}: {at + k} > {self.P.shape[0]}")
+        pb = self.P.element_size() * 4
+        o = 0
+        self.P[at:at + k] = rows[:, o:o + pb].contiguous().view(self.P.dtype).reshape(k, 4)
+        o += pb
+        self.V[at:at + k] = rows[:, o:o + pb].contiguous().view(self.V.dtype).reshape(k, 4)
+        o += pb
+        gid = rows[:, o:o + 4].contiguous().view(torch.int32).reshape(k)
+        self.G[at:at + k] = gid
+        o += 4
+        if with_rng and self.R is not None:
+            self.R[gid.long()] = rows[:, o:o + 16].contiguous().view(torch.int64).reshape(k, 2)
+        return k
+
+    # ------------------------------------------------------------------ one step
+    def exchange_halo(self) -> None:
+        n = self.n_own
+        col = self.columns(self.P[:n, 0])
+        to_left = (col >= self.lo) & (col < self.lo + HALO) if self.rank > 0 else torch.zeros_like(col, dtype=torch.bool)
+        to_right = (col >= self.hi - HALO) & (col < self.hi) if self.rank < self.world - 1 \
+            else torch.zeros_like(col, dtype=torch.bool)
+        il, ir = torch.nonzero(to_left).flatten(), torch.nonzero(to_right).flatten()
+        idx = torch.cat([il, ir])
+        dest = torch.cat([torch.full_like(il, self.rank - 1), torch.full_like(ir, self.rank + 1)])
+        got = self._exchange(self._pack(idx, with_rng=False), dest)
+        self.n_local = n + self._unpack(got, n, with_rng=False)
+        self.stats["halo_sent"] += int(len(idx))
+
+    def migrate(self) -> None:
+        n = self.n_own
+        col = self.columns(self.P[:n, 0])
+        dest = torch.where(col >= 0, self.owner_of(col), torch.full_like(col, self.rank))
+        leave = torch.nonzero(dest != self.rank).flatten()
+        got = self._exchange(self._pack(leave, with_rng=True), dest[leave])
+        if len(leave):
+            keep = torch.nonzero(dest == self.rank).flatten()
+            k = len(keep)
+            self.P[:k] = self.P[keep]
+            self.V[:k] = self.V[keep]
+            self.G[:k] = self.G[keep]
+            n = k
+        self.n_own = n + self._unpack(got, n, with_rng=True)
+        self.n_local = self.n_own
+        self.stats["migrated"] += int(len(leave))
+
+    def step(self, n_steps: int = 1) -> None:
+        for _ in range(n_steps):
+            self.exchange_halo()
+            self._local_step(self.n_own, self.n_local)
+            self.migrate()
+            self.stats["steps"] += 1
+
+    # ------------------------------------------------------------------ loading / gathering
+    def load_global(self, position: np.ndarray, velocity: np.ndarray) -> None:
+        """Every rank passes the same full start state and keeps the particles of its slab (global id = row)."""
+        pos = torch.as_tensor(np.ascontiguousarray(position))
+        col = self.columns(pos[:, 0])
+        mine = torch.nonzero(torch.where(col >= 0, self.owner_of(col), torch.zeros_like(col)) == self.rank).flatten()
+        k = len(mine)
+        if k > self.P.shape[0]:
+            raise RuntimeError(f"slab capacity exceeded on rank {self.rank}: {k} > {self.P.shape[0]}")
+        dev, dt = self.P.device, self.P.dtype
+        self.P[:k, :3] = pos[mine].to(dt).to(dev)
+        self.P[:k, 3] = 0
+        self.V[:k, :3] = torch.as_tensor(np.ascontiguousarray(velocity))[mine].to(dt).to(dev)
+        self.V[:k, 3] = 0
+        self.G[:k] = mine.to(torch.int32).to(dev)
+        self.n_own = self.n_local = k
+
+    def gather_global(self, n_global: int):
+        """All ranks -> every rank: (position, velocity, density) fp64 arrays in global-id order."""
+        n = self.n_own
+        rows = torch.cat([self.P[:n].to(torch.float64), self.V[:n, :3].to(torch.float64),
+                          self.G[:n].to(torch.float64)[:, None]], dim=1).contiguous()
+        if self.world > 1:
+            counts = torch.tensor([n], dtype=torch.int64, device=rows.device)
+            allc = [torch.empty_like(counts) for _ in range(self.world)]
+            dist.all_gather(allc, counts, group=self.group)
+            sizes = [int(c.item()) for c in allc]
+            pad = torch.zeros((max(sizes), 8), dtype=torch.float64, device=rows.device)   # equal sizes for all_gather
+            pad[:n] = rows
+            bufs = [torch.empty_like(pad) for _ in allc]
+            dist.all_gather(bufs, pad, group=self.group)
+            rows = torch.cat([b[:k] for b, k in zip(bufs, sizes)])
+        rows = rows.cpu().numpy()
+        gid = rows[:, 7].astype(np.int64)
+        assert len(gid) == n_global and len(np.unique(gid)) == n_global, "particles lost or duplicated"
+        pos, vel, rho = np.empty((n_global, 3)), np.empty((n_global, 3)), np.empty(n_global)
+        pos[gid], rho[gid], vel[gid] = rows[:, :3], rows[:, 3], rows[:, 4:7]
+        return pos, vel, rho
+
+    def count_global(self) -> int:
+        c = torch.tensor([self.n_own], dtype=torch.int64, device=self.P.device)
+        if self.world > 1:
+            dist.all_reduce(c, group=self.group)
+        return int(c.item())
+
+
+class _CudaBuffer:
+    """Zero-copy view of a raw device pointer for torch.as_tensor (__cuda_array_interface__ v2)."""
+
+    def __init__(self, ptr: int, shape, typestr: str):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+
+
+class GpuSlabRunner(SlabRunner):
+    """SlabRunner over the device buffers of one libsph_b200 handle in x-slab mode."""
+
+    def __init__(self, params, constants=None, *, capacity: int, bounds: Sequence[int], device: int = 0,
+                 cuda_stream: Optional[int] = None, group=None):
+        from . import _lib
+        from .strategy import SphConstants
+        self._lib = _lib.load()
+        self._chk = _lib.check
+        cst = constants or SphConstants()
+        space = np.asarray(params.space_size, np.float64).reshape(3)
+        voxel = np.asarray(params.voxel_size, np.float64).reshape(3)
+        n_cols = int(np.ceil(space[0] / voxel[0]))
+        super().__init__(n_cols, float(voxel[0]), bounds, group)
+        self.n_global = int(params.particle_count)
+        p = _lib.SphParams()
+        p.particle_count = int(capacity)
+        p.mode = _lib.MODE_PIPE if cst.mode.upper() == "PIPE" else _lib.MODE_BOX
+        p.h, p.mass, p.rho0, p.k, p.visc, p.damp = cst.h, cst.mass, cst.rho0, cst.k, cst.visc, cst.damp
+        p.dt = 1 / params.fps
+        ext = np.asarray(params.external_force, np.float64).reshape(3)
+        for d in range(3):
+            p.external_force[d], p.space_size[d], p.voxel_size[d] = ext[d], space[d], voxel[d]
+        p.max_neighbours = cst.max_neighbours
+        p.flags = _lib.FLAG_SLAB | _lib.FLAG_NO_GRAPH
+        p.rng_seed = cst.rng_seed
+        self._h = C.c_void_p()
+        self._chk(self._lib.sph_create(C.byref(p), int(device), C.byref(self._h)))
+        torch.cuda.set_device(device)
+        if cuda_stream is None:   # the torch ops of the exchange and the engine kernels must share one stream
+            cuda_stream = torch.cuda.current_stream().cuda_stream
+        self._chk(self._lib.sph_set_stream(self._h, C.c_void_p(int(cuda_stream))))
+        if p.mode == _lib.MODE_PIPE:
+            table = np.ascontiguousarray(params.pipe.to_numpy(), dtype=np.float64)
+            self._chk(self._lib.sph_set_pipe(self._h, table.ctypes.data, table.shape[0]))
+        self._chk(self._lib.sph_slab_configure(self._h, self.lo, self.hi, self.n_global))
+        dev = torch.device("cuda", device)
+        cap = int(capacity)
+
+        def view(which, shape, typestr, dtype):
+            ptr, _ = C.c_void_p(), None
+            cnt = C.c_int64()
+            self._chk(self._lib.sph_device_ptr(self._h, which, C.byref(ptr), C.byref(cnt)))
+            return torch.as_tensor(_CudaBuffer(ptr.value, shape, typestr), device=dev).view(dtype)
+
+        self.P = view(0, (cap, 4), "<f4", torch.float32)
+        self.V = view(1, (cap, 4), "<f4", torch.float32)
+        self.G = view(4, (cap,), "<i4", torch.int32)
+        self.R = view(5, (self.n_global, 2), "<i8", torch.int64) if p.mode == _lib.MODE_PIPE else None
+
+    def _local_step(self, n_own: int, n_local: int) -> None:
+        self._chk(self._lib.sph_slab_step(self._h, int(n_own), int(n_local)))
+
+    def launch_count(self) -> int:
+        return int(self._lib.sph_launch_count(self._h))
+
+    def synchronize(self):
+        self._chk(self._lib.sph_sync(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.P = self.V = self.G = self.R = None
+            self._lib.sph_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

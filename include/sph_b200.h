@@ -33,6 +33,8 @@ extern "C" {
 #define SPH_FLAG_RECORD_NEIGHBOUR_COUNTS 1u /* accepted for compatibility: neighbour counts are always kept (1 B/particle) */
 #define SPH_FLAG_RECORD_TERMS 2u            /* force sweep also stores the pressure and viscosity terms (parity tap)  */
 #define SPH_FLAG_NO_GRAPH 4u                /* launch kernels eagerly instead of replaying a CUDA graph             */
+#define SPH_FLAG_SLAB 8u                    /* x-slab mode (one handle per GPU of a multi-GPU run); particle_count is the
+                                               CAPACITY of the local arrays (owned + ghost particles)              */
 
 /* Replaces: SimulationParameters (common/data_classes.py:70-78) + the module constants of config.py:18-36 that the
  * reference freezes into its kernels at import time (base_kernels.py:2, voxel_kernels.py:5). */
@@ -121,6 +123,16 @@ int sph_sync(sph_handle_t h);
 int sph_save_state(sph_handle_t h);
 int sph_restore_state(sph_handle_t h);
 
+/* ---- x-slab domain decomposition (no reference counterpart: the reference is single-GPU) --------------------------
+ * The handle owns the cell columns [x_lo, x_hi) of the global grid and keeps a two-column ghost halo on each side.
+ * The host layer (cuda_sph_b200/slab.py, torch.distributed) writes owned particles to local indices [0, n_own) and
+ * ghost particles to [n_own, n_local) of the master arrays (sph_device_ptr 0/1) and their global ids to buffer 4,
+ * then calls sph_slab_step: hash -> sort -> in-cell order by global id -> cell table + reorder -> density for owned
+ * and first-ghost columns -> forces / integrate / collide for owned particles only.  n_global sizes the xoroshiro
+ * state table (PIPE mode; states are indexed by global particle id). */
+int sph_slab_configure(sph_handle_t h, int32_t x_lo, int32_t x_hi, int64_t n_global);
+int sph_slab_step(sph_handle_t h, int32_t n_own, int32_t n_local);
+
 /* ---- parity taps: state of the most recent step --------------------------------------------------------------- */
 int sph_get_keys(sph_handle_t h, int32_t *keys);                 /* self.voxels            voxel_sph_strategy.py:82 */
 int sph_get_sorted_ids(sph_handle_t h, int32_t *ids);            /* voxel_particle_map['particle_id']        :85-88 */
@@ -136,7 +148,8 @@ int64_t sph_n_cells(sph_handle_t h);
 int sph_cell_dims(sph_handle_t h, int32_t *ceil3, int32_t *trunc3);
 
 /* Device pointers for zero-copy wrapping (torch / __cuda_array_interface__).  which: 0 = master position float4[N]
- * (x,y,z,density), 1 = master velocity float4[N], 2 = sorted ids int32[N], 3 = sorted position float4[N]. */
+ * (x,y,z,density), 1 = master velocity float4[N], 2 = sorted ids int32[N], 3 = sorted position float4[N],
+ * 4 = global ids int32[capacity] (x-slab mode), 5 = xoroshiro states uint64[2 * count] (PIPE mode). */
 int sph_device_ptr(sph_handle_t h, int32_t which, void **ptr, int64_t *n_elements);
 
 /* Total kernels/memsets launched by this handle so far (bench.py's "gpu_launches"). */

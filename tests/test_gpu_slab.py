@@ -1,0 +1,75 @@
+"""Multi-GPU x-slab run vs the single-GPU engine (needs >= 2 GPUs; NCCL).  The slab run must reproduce the single-GPU
+engine BITWISE (same neighbour lists, same summation order), and therefore the reference within the fp32 tolerance."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, mode, n, steps, out_path):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from cuda_sph_b200 import SphConstants
+        from cuda_sph_b200.slab import GpuSlabRunner, equal_count_bounds
+        from tests.test_gpu_slab import _case
+        params, st = _case(mode, n)
+        n_cols = int(np.ceil(params.space_size[0] / params.voxel_size[0]))
+        cols = np.clip((st.position[:, 0] / params.voxel_size[0]).astype(np.int64), 0, n_cols - 1)
+        bounds = equal_count_bounds(np.bincount(cols, minlength=n_cols), world)
+        run = GpuSlabRunner(params, SphConstants(mode=mode), capacity=2 * n, bounds=bounds, device=rank)
+        run.load_global(st.position, st.velocity)
+        run.step(steps)
+        assert run.count_global() == n
+        pos, vel, rho = run.gather_global(n)
+        if rank == 0:
+            np.savez(out_path, pos=pos, vel=vel, rho=rho, halo=run.stats["halo_sent"], migrated=run.stats["migrated"])
+        run.close()
+    finally:
+        dist.destroy_process_group()
+
+
+def _case(mode, n):
+    from cuda_sph_b200 import config, workloads
+    if mode == "BOX":
+        return workloads.uniform_box(n, 8.0, seed=21)
+    params = config.pipe_params(n)
+    st = config.start_state_inside_pipe(n, params.pipe, seed=22)
+    vel = np.random.default_rng(23).uniform(-20, 20, (n, 3))
+    vel[:, 0] += 60.0
+    return params, type(st)(st.position, vel.astype(np.float32).astype(np.float64), st.density)
+
+
+@pytest.mark.parametrize("mode,n", [("BOX", 200000), ("PIPE", 20000)])
+def test_two_gpu_slabs_equal_single_gpu(tmp_path, mode, n):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    from cuda_sph_b200 import B200SPHStrategy, SphConstants
+    steps = 3
+    out = str(tmp_path / "slab.npz")
+    mp.spawn(_worker, args=(2, _free_port(), mode, n, steps, out), nprocs=2, join=True)
+    got = np.load(out)
+    params, st = _case(mode, n)
+    s = B200SPHStrategy(params, SphConstants(mode=mode))
+    s.upload(st)
+    s.step(steps)
+    ref = s.download()
+    s.close()
+    eq = lambda a, b: bool(np.all((a == b) | (np.isnan(a) & np.isnan(b))))  # noqa: E731
+    assert eq(got["pos"], ref.position)
+    assert eq(got["vel"], ref.velocity)
+    assert eq(got["rho"], ref.density)
+    assert got["halo"] > 0 and got["migrated"] > 0

@@ -1,0 +1,142 @@
+"""x-slab decomposition logic on CPU: world_size 2 and 3 over gloo, with the fp64 oracle as the local step.
+
+The decomposition (two-column halos, ownership, migration to arbitrary ranks, in-cell order by global id, xoroshiro
+state travelling with a particle) must reproduce the single-domain oracle BITWISE after several steps -- the physics
+is violent enough (speeds of 1e2..1e5 cells per step) that particles cross several slabs per step."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from cuda_sph_b200 import config, workloads
+from cuda_sph_b200.slab import HALO, SlabRunner, equal_count_bounds
+from oracle import oracle as orc
+from tests.helpers import same
+
+
+class OracleSlabRunner(SlabRunner):
+    """SlabRunner whose local step is the CPU oracle on (owned + ghost) particles."""
+
+    def __init__(self, P: orc.OracleParams, n_global, capacity, n_cols, bounds, pipe_mode):
+        super().__init__(n_cols, P.voxel[0], bounds)
+        self.oparams = P
+        self.P = torch.zeros((capacity, 4), dtype=torch.float64)
+        self.V = torch.zeros((capacity, 4), dtype=torch.float64)
+        self.G = torch.zeros(capacity, dtype=torch.int32)
+        self.R = torch.from_numpy(orc.rng_init(n_global).view(np.int64).copy()) if pipe_mode else None
+
+    def _local_step(self, n_own, n_local):
+        if n_local == 0:
+            return
+        gid = self.G[:n_local].numpy()
+        order = np.argsort(gid, kind="stable")      # local row order == global id order, like the single domain
+        inv = np.empty_like(order)
+        inv[order] = np.arange(n_local)
+        pos = self.P[:n_local, :3].numpy()[order]
+        vel = self.V[:n_local, :3].numpy()[order]
+        P = orc.OracleParams(**{**self.oparams.__dict__, "n": n_local, "_keep": []})
+        rng = None
+        if self.R is not None:
+            rng = self.R.numpy()[gid[order]].view(np.uint64).copy()
+        r = orc.step(P, pos, vel, rng=rng, light=True)
+        own = inv[:n_own]
+        self.P[:n_own, :3] = torch.from_numpy(r.position[own])
+        self.P[:n_own, 3] = torch.from_numpy(r.density[own])
+        self.V[:n_own, :3] = torch.from_numpy(r.velocity[own])
+        if self.R is not None:
+            self.R[torch.from_numpy(gid[:n_own].astype(np.int64))] = torch.from_numpy(rng[own].view(np.int64))
+
+
+def _case(mode):
+    if mode == "BOX":
+        n = 3000
+        params, st = workloads.uniform_box(n, 8.0, seed=11)
+        P = orc.OracleParams(n=n, mode="BOX", space=tuple(params.space_size), dt=1 / params.fps)
+    else:
+        n = 2500
+        params = config.pipe_params(n)
+        st = config.start_state_inside_pipe(n, params.pipe, seed=12)
+        rng = np.random.default_rng(13)
+        vel = rng.uniform(-20, 20, (n, 3))
+        vel[:, 0] += 60.0                                   # strong flow towards the outlet -> recycles
+        st = type(st)(st.position, vel.astype(np.float32).astype(np.float64), st.density)
+        P = orc.OracleParams(n=n, mode="PIPE", space=tuple(params.space_size), ext=tuple(params.external_force),
+                             dt=1 / params.fps, pipe=params.pipe.to_numpy())
+    return n, params, st, P
+
+
+def _worker(rank, world, port, mode, steps, out_path):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        orc.set_exact_pow(False)
+        orc.set_num_threads(1)
+        n, params, st, P = _case(mode)
+        n_cols = int(np.ceil(params.space_size[0] / params.voxel_size[0]))
+        cols = np.clip((st.position[:, 0] / params.voxel_size[0]).astype(np.int64), 0, n_cols - 1)
+        bounds = equal_count_bounds(np.bincount(cols, minlength=n_cols), world)
+        run = OracleSlabRunner(P, n, capacity=2 * n, n_cols=n_cols, bounds=bounds, pipe_mode=(mode == "PIPE"))
+        run.load_global(st.position, st.velocity)
+        assert run.count_global() == n
+        run.step(steps)
+        assert run.count_global() == n                       # nothing lost, nothing duplicated
+        pos, vel, rho = run.gather_global(n)
+        stats = torch.tensor([run.stats["halo_sent"], run.stats["migrated"]])
+        dist.all_reduce(stats)
+        if rank == 0:
+            np.savez(out_path, pos=pos, vel=vel, rho=rho, halo=int(stats[0]), migrated=int(stats[1]),
+                     bounds=np.asarray(bounds))
+    finally:
+        dist.destroy_process_group()
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+@pytest.mark.parametrize("world,mode", [(2, "BOX"), (3, "BOX"), (2, "PIPE")])
+def test_slab_decomposition_matches_single_domain_bitwise(tmp_path, world, mode):
+    steps = 3
+    out = str(tmp_path / "slab.npz")
+    mp.spawn(_worker, args=(world, _free_port(), mode, steps, out), nprocs=world, join=True)
+    got = np.load(out)
+    # single-domain oracle
+    orc.set_exact_pow(False)
+    n, params, st, P = _case(mode)
+    rng = orc.rng_init(n) if mode == "PIPE" else None
+    pos, vel, rho = st.position, st.velocity, None
+    for _ in range(steps):
+        r = orc.step(P, pos, vel, rng=rng, light=True)
+        pos, vel, rho = r.position, r.velocity, r.density
+    assert same(got["pos"], pos)
+    assert same(got["vel"], vel)
+    assert same(got["rho"], rho)
+    assert got["halo"] > 0 and got["migrated"] > 0           # the exchanges really happened
+    assert all(b - a >= HALO for a, b in zip(got["bounds"][:-1], got["bounds"][1:]))
+
+
+def test_equal_count_bounds():
+    hist = np.zeros(75, np.int64)
+    hist[:8] = 1000                                          # dam-break column: everything in the first columns
+    b = equal_count_bounds(hist, 4)
+    assert b == [0, 2, 4, 6, 75]
+    b = equal_count_bounds(np.full(40, 10), 8)
+    assert b == [0, 5, 10, 15, 20, 25, 30, 35, 40]
+    with pytest.raises(ValueError):
+        equal_count_bounds(np.ones(6), 4)
+
+
+def test_column_and_owner_mapping():
+    run = SlabRunner.__new__(SlabRunner)
+    run.voxel_x, run.n_cols, run.bounds = 2.0, 10, [0, 3, 7, 10]
+    x = torch.tensor([0.0, 1.99, 2.0, -0.5, 5.99, 6.0, 13.99, 14.0, 19.99, float("nan"), float("inf"), 25.0])
+    col = run.columns(x)
+    assert col.tolist() == [0, 0, 1, 0, 2, 3, 6, 7, 9, -1, -1, 12]
+    assert run.owner_of(col[:9]).tolist() == [0, 0, 0, 0, 0, 1, 1, 2, 2]
+    assert run.owner_of(torch.tensor([12])).tolist() == [2]   # clamped
