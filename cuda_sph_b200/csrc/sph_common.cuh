@@ -55,7 +55,8 @@ __device__ __forceinline__ bool cell_of(const GridDesc &g, float x, float y, flo
 __device__ __forceinline__ uint32_t key_of(const GridDesc &g, float x, float y, float z) {
     int vx, vy, vz;
     if (!cell_of(g, x, y, z, vx, vy, vz)) return (uint32_t)g.ncells;
-    if (g.strict_x && (vx < g.xoff || vx >= g.xoff + g.wk)) return (uint32_t)g.ncells;
+    // x-slab mode: no x aliasing across slabs -- a column outside the domain or the local table is dead
+    if (g.strict_x && (vx < 0 || vx >= g.tx || vx < g.xoff || vx >= g.xoff + g.wk)) return (uint32_t)g.ncells;
     const long long k = (long long)vx - g.xoff + (long long)vy * g.wk + (long long)vz * g.wk * g.hk;
     return (k >= 0 && k < g.ncells) ? (uint32_t)k : (uint32_t)g.ncells;
 }
