@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsph_b200.so")
 SOURCES = ["sph_engine.cu"]
-HEADERS = ["sph_common.cuh", "radix_sort.cuh", "collide.cuh", "sph_kernels.cuh", "sweep.cuh", "../../include/sph_b200.h"]
+HEADERS = ["sph_common.cuh", "radix_sort.cuh", "collide.cuh", "sph_kernels.cuh", "sweep.cuh", "sweep_rows.cuh", "../../include/sph_b200.h"]
 
 
 def nvcc_path() -> str:

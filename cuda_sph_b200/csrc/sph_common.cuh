@@ -20,6 +20,8 @@ struct GridDesc {
     // x-slab decomposition (multi-GPU).  Single GPU: strict_x = 0, own_lo = INT_MIN/2, own_hi = INT_MAX/2.
     int32_t strict_x;    // 1: a particle whose x column falls outside the local table [xoff, xoff + wk) is dead
     int32_t own_lo, own_hi;  // owned x columns [own_lo, own_hi); density is also computed one column beyond
+    int32_t aligned;     // 1: trunc dims == ceil dims (no quirk Q2), the row-staged sweeps apply; 0: every particle walks
+    float inv_voxel[3];  // fp32 1 / voxel, only for the cheap "strictly inside its cell" pre-test
 };
 
 struct StepConsts {

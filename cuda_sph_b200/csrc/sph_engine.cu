@@ -6,6 +6,7 @@
 #include <climits>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -14,6 +15,7 @@
 #include "radix_sort.cuh"
 #include "sph_kernels.cuh"
 #include "sweep.cuh"
+#include "sweep_rows.cuh"
 
 using namespace sph;
 
@@ -59,6 +61,7 @@ struct SphEngine {
     int64_t rng_count = 0;
     // x-slab mode (multi-GPU)
     bool slab = false;
+    bool rows_sweeps = true;      // row-staged sweeps (sweep_rows.cuh); false: per-warp tiles (sweep.cuh), SPH_SWEEP=warp
     int32_t *gid = nullptr;       // global particle id per local index
     int32_t slab_lo = 0, slab_hi = 0;
     int64_t cell_capacity = 0;    // entries allocated in cell_range
@@ -181,6 +184,12 @@ int sph_create(const SphParams *params, int device, sph_handle_t *out) {
     e->grid.strict_x = 0;
     e->grid.own_lo = INT32_MIN / 2;
     e->grid.own_hi = INT32_MAX / 2;
+    e->grid.aligned = 1;
+    for (int d = 0; d < 3; ++d) {
+        if (e->ceil_dims[d] != e->trunc_dims[d]) e->grid.aligned = 0;
+        e->grid.inv_voxel[d] = (float)(1.0 / params->voxel_size[d]);
+    }
+    if (const char *sw = getenv("SPH_SWEEP")) e->rows_sweeps = strcmp(sw, "warp") != 0;
     e->slab = (params->flags & SPH_FLAG_SLAB) != 0;
     long long table_cells = ncells;
     if (e->slab) {
@@ -291,6 +300,11 @@ int sph_create(const SphParams *params, int device, sph_handle_t *out) {
     }
     e->own_stream = true;
     for (auto &ev : e->ev) cudaEventCreate(&ev);
+    cudaFuncSetAttribute(density_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DensityRowsSmem));
+    cudaFuncSetAttribute(force_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)sizeof(ForceRowsSmem));
+    cudaFuncSetAttribute(force_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)sizeof(ForceRowsSmem));
     e->launches_per_step = 1 + 3 * e->passes + 1 + 1 + 1 + 1;
     if (cudaDeviceSynchronize() != cudaSuccess) {
         sph_destroy(e);
@@ -438,13 +452,23 @@ static int enqueue_step(SphEngine *e, bool timed, int n, int n_own) {
     sa.gid = e->slab ? e->gid : nullptr;
     sa.n = n;
     sa.n_own = n_own;
-    const int gsw = (n + SW_THREADS - 1) / SW_THREADS;
-    density_kernel<<<gsw, SW_THREADS, 0, s>>>(sa, e->grid, e->consts);
-    if (timed) cudaEventRecord(e->ev[4], s);
-    if (e->spress)
-        force_kernel<true><<<gsw, SW_THREADS, 0, s>>>(sa, e->grid, e->consts);
-    else
-        force_kernel<false><<<gsw, SW_THREADS, 0, s>>>(sa, e->grid, e->consts);
+    if (e->rows_sweeps) {
+        const int grb = (n + RB_THREADS - 1) / RB_THREADS;
+        density_rows_kernel<<<grb, RB_THREADS, sizeof(DensityRowsSmem), s>>>(sa, e->grid, e->consts);
+        if (timed) cudaEventRecord(e->ev[4], s);
+        if (e->spress)
+            force_rows_kernel<true><<<grb, RB_THREADS, sizeof(ForceRowsSmem), s>>>(sa, e->grid, e->consts);
+        else
+            force_rows_kernel<false><<<grb, RB_THREADS, sizeof(ForceRowsSmem), s>>>(sa, e->grid, e->consts);
+    } else {
+        const int gsw = (n + SW_THREADS - 1) / SW_THREADS;
+        density_kernel<<<gsw, SW_THREADS, 0, s>>>(sa, e->grid, e->consts);
+        if (timed) cudaEventRecord(e->ev[4], s);
+        if (e->spress)
+            force_kernel<true><<<gsw, SW_THREADS, 0, s>>>(sa, e->grid, e->consts);
+        else
+            force_kernel<false><<<gsw, SW_THREADS, 0, s>>>(sa, e->grid, e->consts);
+    }
     if (timed) cudaEventRecord(e->ev[5], s);
     CK(cudaGetLastError());
     return 0;

@@ -108,7 +108,7 @@ struct ForceAcc {
 
 // integrating_kernel + collision kernel in fp64 (base_kernels.py:30-98), scatter to the id-ordered master arrays.
 template <bool RECORD_TERMS>
-__device__ __forceinline__ void finish_particle(const SweepArgs &a, const StepConsts &c, int t, const float4 pi,
+__device__ __noinline__ void finish_particle(const SweepArgs &a, const StepConsts &c, int t, const float4 pi,
                                                 const float4 vi, float rho_i, ForceAcc f) {
     if (f.any) {  // with no neighbour besides self the reference's sums stay exactly 0 (and rho_i is 0)
         const float s = c.mass_visc / rho_i;

@@ -1,0 +1,566 @@
+// Neighbour sweeps, "row-staged" organisation (sm_100a): density_rows_kernel and force_rows_kernel.
+//
+// Reference semantics (voxel_kernels.py:29-85): a particle's neighbour list is the first 32 candidates (self included)
+// that pass sqrt(r^2) <= INF_R when the <= 27 cells around it are walked dx outermost / dz innermost and every cell in
+// ascending particle id; all sums run over that list in order.  The sorted arrays are cell-contiguous with ascending id
+// inside a cell and the cell key is x-fastest, so for a group of consecutive sorted particles the candidates of ALL
+// their cells lie in 9 contiguous ranges of the sorted arrays ("rows": one per (dy, dz), covering the x-neighbours).
+//
+// One CTA = 128 consecutive sorted particles:
+//   setup   find the CTA's non-empty cells, fetch their 27 cell ranges, take per-row min/max -> 9 row ranges; ONE
+//           THREAD issues 9 (density) / 18 (force) 1-D TMA bulk copies (cp.async.bulk -> UBLKCP) that land the rows in
+//           shared memory and signal an mbarrier; meanwhile the warps build, per cell, the map from the cell's
+//           candidate sequence ("virtual list") to row slots (`vmap`, 2 B per candidate).
+//   density phase 1 (warp-cooperative, one particle at a time): the 32 lanes test 64 candidates per round straight
+//           from the staged rows and keep only the two ballots; a particle stops after the round in which it reaches
+//           32 hits -- nobody idles behind a slower neighbour and no lane is lost at low particles-per-cell.  The test
+//           is the fp32 superset r2 < h^2 (1 + 1e-5).
+//   density phase 2 (lane = particle): walks its own ballots in order, re-evaluates the accepted candidates (fp64
+//           predicate inside the rounding band -> neighbour lists are bit-identical to the fp64 reference), writes the
+//           list of row SLOTS, accumulates the poly6 density, and publishes rho, the count, the list and the
+//           per-particle factors p/rho^2 and LAP_W_CONST/rho (into the .w lanes of the sorted position / velocity).
+//   force   same setup (positions + velocities), then lane = particle runs down its slot list: 2 LDS.128 + ~40 FP
+//           instructions per pair, no reductions, list order == the reference's summation order; fp64 integrate +
+//           collide epilogue and scatter to the id-ordered master arrays (finish_particle, sweep.cuh).
+// Both kernels derive the row layout from (sorted keys, cell table) with the same code, so a slot means the same thing
+// in both.  A CTA whose rows do not fit shared memory falls back to four 32-particle passes; a pass that still does
+// not fit, particles whose own cell differs from their sort cell (aliased keys, reference quirk Q5), grids whose
+// trunc and ceil dims differ (Q2) and particles that exhaust their ballot budget take the plain one-thread walk of
+// sweep.cuh (exact, slow, rare).
+#pragma once
+#include "sweep.cuh"
+
+namespace sph {
+
+constexpr int RB_THREADS = 128;   // threads == particles per CTA
+constexpr int RB_WARPS = RB_THREADS / 32;
+constexpr int RB_CAP = 2048;      // row slots per CTA pass (candidates staged in shared memory)
+constexpr int RB_MAXC = 64;       // non-empty cells per CTA pass
+constexpr int RB_VCAP = 6144;     // vmap entries per CTA pass
+constexpr int RB_MR = 12;         // ballot rounds (64 candidates each) kept per particle
+constexpr int RB_MSTRIDE = 13;    // uint2 per ballot row (26 words: conflict-free LDS.64 per half warp)
+constexpr int RB_LSTRIDE = 34;    // uint16 per list row (17 words: conflict-free rows)
+
+// ---- mbarrier + 1-D TMA bulk copy -----------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(void *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(void *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, void *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(void *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+
+__device__ __forceinline__ uint32_t lanemask_le_() {
+    uint32_t m;
+    asm("mov.u32 %0, %%lanemask_le;" : "=r"(m));
+    return m;
+}
+
+// ---- per-CTA plan (shared memory) ---------------------------------------------------------------------------------------
+struct RowPlan {
+    unsigned long long mbar;
+    int row_lo[9], row_hi[9];   // sorted-index range of each row (min / max over the CTA's cells)
+    int row_base[10];           // first slot of each row; [9] = slots used
+    int wcount[RB_WARPS];
+    int ncell;                  // non-empty cells of the pass
+    int fits;
+    uint32_t ckey[RB_MAXC];     // key of local cell ci
+    int start13[RB_MAXC];       // sorted index of the first particle of the cell
+    int slot13[RB_MAXC];        // its row slot
+    int vbase[RB_MAXC];         // first vmap entry of the cell            (density only)
+    int Tc[RB_MAXC];            // length of the cell's virtual list        (density only)
+};
+
+struct DensityRowsSmem {
+    float4 rows[RB_CAP + 1];                        // [RB_CAP] = far-away sentinel candidate
+    uint16_t vmap[RB_VCAP];
+    union {
+        uint2 mask[RB_THREADS * RB_MSTRIDE];        // phase 1 -> phase 2 ballots
+        struct {                                    // setup only (dead before phase 1)
+            int seg_start[RB_MAXC * 27];
+            uint16_t seg_off[RB_MAXC * 28];
+        } t;
+    } u;
+    uint16_t list[RB_THREADS * RB_LSTRIDE];
+    RowPlan plan;
+};
+
+struct ForceRowsSmem {
+    float4 rpos[RB_CAP + 1];   // (x, y, z, p/rho^2)
+    float4 rvel[RB_CAP + 1];   // (vx, vy, vz, LAP_W_CONST/rho)
+    RowPlan plan;
+};
+
+// Neighbour cell `s` (0..26, dx outermost, dz innermost: voxel_kernels.py:46-48) of cell (cx, cy, cz): range of the
+// sorted arrays, (0, 0) if the cell is outside the domain / the local table.
+__device__ __forceinline__ int2 neighbour_range(const SweepArgs &a, const GridDesc &g, int s, int cx, int cy, int cz) {
+    const int x = cx + s / 9 - 1, y = cy + (s / 3) % 3 - 1, z = cz + s % 3 - 1;
+    if (x >= 0 && x < g.tx && y >= 0 && y < g.ty && z >= 0 && z < g.tz) {
+        const long long cl = (long long)x - g.xoff + (long long)y * g.wn + (long long)z * g.wn * g.hn;
+        if (cl >= 0 && cl < g.ncells) return __ldg(&a.cell_range[cl]);
+    }
+    return make_int2(0, 0);
+}
+
+// Setup of one pass over the CTA-local particles [j0, j1).  Returns false (CTA-uniform) if the pass does not fit; then
+// nothing was issued.  On success the TMA copies are in flight on plan.mbar (wait with the caller's parity).
+//   key, live : this thread's particle (j = threadIdx.x, sorted index t = p0 + j)
+//   ci        : out, local cell index of this thread's particle (valid if live and in range)
+template <bool DENSITY>
+__device__ __forceinline__ bool rows_setup(const SweepArgs &a, const GridDesc &g, RowPlan &plan, float4 *rows_a,
+                                           float4 *rows_b, DensityRowsSmem *ds, int j0, int j1, int t, uint32_t key,
+                                           bool live, int &ci) {
+    const int j = threadIdx.x, lane = j & 31, warp = j >> 5;
+    const bool mine = live && j >= j0 && j < j1;
+    bool first = false;
+    if (mine) first = (j == j0) || (a.skeys[t - 1] != key);
+    const unsigned bal = __ballot_sync(FULL, first);
+    if (lane == 0) plan.wcount[warp] = __popc(bal);
+    if (j < 9) {
+        plan.row_lo[j] = INT_MAX;
+        plan.row_hi[j] = 0;
+    }
+    __syncthreads();
+    int off = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < RB_WARPS; ++w) {
+        const int c = plan.wcount[w];
+        if (w < warp) off += c;
+        total += c;
+    }
+    ci = off + __popc(bal & lanemask_le_()) - 1;
+    if (total > RB_MAXC) {
+        __syncthreads();   // wcount is rewritten by the next pass
+        return false;
+    }
+    if (first) plan.ckey[ci] = key;
+    __syncthreads();
+
+    // ---- per cell: the 27 neighbour ranges, row min / max, virtual-list offsets ----
+    for (int c = warp; c < total; c += RB_WARPS) {
+        int cx, cy, cz;
+        decode_cell(g, plan.ckey[c], cx, cy, cz);
+        int2 r = make_int2(0, 0);
+        if (lane < 27) r = neighbour_range(a, g, lane, cx, cy, cz);
+        const int cnt = r.y - r.x;
+        if (cnt > 0) {
+            atomicMin(&plan.row_lo[lane % 9], r.x);
+            atomicMax(&plan.row_hi[lane % 9], r.y);
+        }
+        if (lane == 13) plan.start13[c] = r.x;
+        if (DENSITY) {
+            int inc = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int u = __shfl_up_sync(FULL, inc, o);
+                if (lane >= o) inc += u;
+            }
+            if (lane < 27) ds->u.t.seg_start[c * 27 + lane] = r.x;
+            if (lane < 28) ds->u.t.seg_off[c * 28 + lane] = (uint16_t)min(inc - cnt, 65535);   // [27] = T (saturated)
+            if (lane == 31) plan.Tc[c] = inc;
+        }
+    }
+    __syncthreads();
+
+    // ---- row bases, vmap bases, capacity check, TMA issue (warp 0) ----
+    if (warp == 0) {
+        const int len = (lane < 9) ? max(plan.row_hi[lane] - plan.row_lo[lane], 0) : 0;
+        int inc = len;
+#pragma unroll
+        for (int o = 1; o < 16; o <<= 1) {
+            const int u = __shfl_up_sync(FULL, inc, o);
+            if (lane >= o) inc += u;
+        }
+        const int slots = __shfl_sync(FULL, inc, 8);
+        if (lane < 9) plan.row_base[lane] = inc - len;
+        bool fits = slots <= RB_CAP;
+        if (DENSITY) {
+            int vtot = 0;
+            for (int base = 0; base < total; base += 32) {
+                const int c = base + lane;
+                const int vlen = (c < total) ? min((plan.Tc[c] + 63) & ~63, RB_MR * 64) : 0;
+                int vi = vlen;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int u = __shfl_up_sync(FULL, vi, o);
+                    if (lane >= o) vi += u;
+                }
+                if (c < total) plan.vbase[c] = vtot + vi - vlen;
+                vtot += __shfl_sync(FULL, vi, 31);
+            }
+            fits = fits && vtot <= RB_VCAP;
+        }
+        if (lane == 0) {
+            plan.row_base[9] = slots;
+            plan.ncell = total;
+            plan.fits = fits ? 1 : 0;
+        }
+        // lane 0 arms the barrier with the byte count of all rows before any copy is issued
+        if (fits && lane == 0) {
+            fence_proxy_async();   // earlier generic-proxy reads of the rows (previous pass) vs. the async-proxy writes
+            mbar_expect_tx(&plan.mbar, (uint32_t)slots * (DENSITY ? 16u : 32u));
+        }
+        __syncwarp();
+        if (fits && lane < 9 && len > 0) {
+            const int base = inc - len, lo = plan.row_lo[lane];
+            bulk_g2s(&rows_a[base], &a.spos[lo], (uint32_t)len * 16u, &plan.mbar);
+            if (!DENSITY) bulk_g2s(&rows_b[base], &a.svel[lo], (uint32_t)len * 16u, &plan.mbar);
+        }
+    }
+    __syncthreads();
+    if (!plan.fits) return false;
+
+    // ---- per cell: slot of the own segment; density: virtual list -> slot map ----
+    for (int c = warp; c < total; c += RB_WARPS) {
+        if (DENSITY) {
+            const int vb = plan.vbase[c], T = plan.Tc[c];
+            const int vlen = min((T + 63) & ~63, RB_MR * 64);
+            if (lane < 27) {
+                const int off0 = ds->u.t.seg_off[c * 28 + lane];
+                const int cnt = (int)ds->u.t.seg_off[c * 28 + lane + 1] - off0;
+                const int start = ds->u.t.seg_start[c * 27 + lane];
+                const int slot0 = plan.row_base[lane % 9] + (start - plan.row_lo[lane % 9]);
+                if (lane == 13) plan.slot13[c] = slot0;
+                uint16_t *dst = ds->vmap + vb + off0;
+                const int m = min(cnt, vlen - off0);
+                for (int l = 0; l < m; ++l) dst[l] = (uint16_t)(slot0 + l);
+            }
+            for (int v = T + lane; v < vlen; v += 32) ds->vmap[vb + v] = (uint16_t)RB_CAP;
+        } else if (lane == 0) {
+            plan.slot13[c] = plan.row_base[4] + (plan.start13[c] - plan.row_lo[4]);
+        }
+    }
+    __syncthreads();
+    return true;
+}
+
+// Does the particle's own cell (from its position, fp64 division + C truncation: voxel_kernels.py:40-41) equal the
+// cell it was sorted into?  Cheap fp32 interior test first; the exact test only near a cell face.
+__device__ __forceinline__ bool own_cell_matches(const GridDesc &g, const float4 &p, int cx, int cy, int cz) {
+    const float fx = p.x * g.inv_voxel[0] - (float)cx, fy = p.y * g.inv_voxel[1] - (float)cy,
+                fz = p.z * g.inv_voxel[2] - (float)cz;
+    const float lo = 1e-3f, hi = 1.f - 1e-3f;
+    if (fx > lo && fx < hi && fy > lo && fy < hi && fz > lo && fz < hi) return true;
+    int vx, vy, vz;
+    return cell_of(g, p.x, p.y, p.z, vx, vy, vz) && vx == cx && vy == cy && vz == cz;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// density_kernel (voxel_kernels.py:108-132) + neighbour lists
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(RB_THREADS, 3)
+density_rows_kernel(const SweepArgs a, const GridDesc g, const StepConsts c) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    DensityRowsSmem &sm = *reinterpret_cast<DensityRowsSmem *>(smem_raw);
+    RowPlan &plan = sm.plan;
+    const int j = threadIdx.x, lane = j & 31, warp = j >> 5;
+    const int p0 = blockIdx.x * RB_THREADS;
+    const int t = p0 + j;
+    const int nb = min(RB_THREADS, a.n - p0);
+    const uint32_t key = (j < nb) ? a.skeys[t] : (uint32_t)g.ncells;
+    const bool live = key != (uint32_t)g.ncells;
+    if (j == 0) {
+        mbar_init(&plan.mbar, 1);
+        fence_mbar_init();
+        sm.rows[RB_CAP] = make_float4(1e18f, 1e18f, 1e18f, 0.f);
+    }
+    if (j < nb && !live) {   // dead particle: no neighbours
+        a.srho[t] = 0.f;
+        a.ncnt[t] = 0;
+    }
+    __syncthreads();
+    if (__syncthreads_count(live) == 0) return;
+
+    // this thread's particle
+    float4 pi = make_float4(0.f, 0.f, 0.f, 0.f);
+    int cx = 0, cy = 0, cz = 0;
+    bool want = false, walk = false;
+    if (live) {
+        pi = a.spos[t];
+        decode_cell(g, key, cx, cy, cz);
+        want = !(cx < g.own_lo - 1 || cx > g.own_hi);   // x-slab: nobody needs the density of the outer ghost column
+        walk = want && (!g.aligned || !own_cell_matches(g, pi, cx, cy, cz));
+    }
+
+    uint32_t parity = 0;
+    int pass = g.aligned ? -1 : 4;   // -1: whole CTA; 0..3: one warp's particles; 4: no staging at all (everyone walks)
+    int j0 = 0, j1 = nb;
+    while (pass < 4) {
+        int ci = 0;
+        const bool ok = rows_setup<true>(a, g, plan, sm.rows, nullptr, &sm, j0, j1, t, key, live, ci);
+        const bool in_pass = live && want && j >= j0 && j < j1;
+        if (ok) {
+            while (!mbar_try_wait(&plan.mbar, parity)) {
+            }
+            parity ^= 1u;
+            const bool active = in_pass && !walk;
+            const int self = active ? plan.slot13[ci] + (t - plan.start13[ci]) : 0;
+            int my_rounds = 0;
+            bool my_more = false;   // phase 1 stopped before the end of the virtual list
+            const bool warp_in = (warp * 32 < j1) && (warp * 32 + 32 > j0);
+            if (warp_in) {
+                // ---- phase 1: one particle at a time, 32 lanes x 2 candidates per round, ballots only ----
+                unsigned todo = __ballot_sync(FULL, active);
+                while (todo) {
+                    const int il = __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    const int cil = __shfl_sync(FULL, ci, il);
+                    const int sslot = __shfl_sync(FULL, self, il);
+                    const int T = plan.Tc[cil];
+                    const int nr = min((T + 63) >> 6, RB_MR);
+                    const float4 p = sm.rows[sslot];
+                    const uint16_t *vm = sm.vmap + plan.vbase[cil] + lane;
+                    uint2 *mrow = sm.u.mask + (warp * 32 + il) * RB_MSTRIDE;
+                    int cnt = 0, q = 0;
+                    for (; q < nr;) {
+                        const float4 c0 = sm.rows[vm[q * 64]], c1 = sm.rows[vm[q * 64 + 32]];
+                        const float dx0 = p.x - c0.x, dy0 = p.y - c0.y, dz0 = p.z - c0.z;
+                        const float dx1 = p.x - c1.x, dy1 = p.y - c1.y, dz1 = p.z - c1.z;
+                        const float r0 = fmaf(dz0, dz0, fmaf(dy0, dy0, dx0 * dx0));
+                        const float r1 = fmaf(dz1, dz1, fmaf(dy1, dy1, dx1 * dx1));
+                        const unsigned m0 = __ballot_sync(FULL, r0 < c.h2_hi), m1 = __ballot_sync(FULL, r1 < c.h2_hi);
+                        if (lane == 0) mrow[q] = make_uint2(m0, m1);
+                        cnt += __popc(m0) + __popc(m1);
+                        ++q;
+                        if (cnt >= kMaxNeighbours) break;
+                    }
+                    if (lane == il) {
+                        my_rounds = q;
+                        my_more = q * 64 < T;
+                    }
+                }
+                __syncwarp();
+                // ---- phase 2: lane = particle, ballots -> exact list + density ----
+                int k = 0;
+                float dens = 0.f;
+                if (active) {
+                    const uint16_t *vm = sm.vmap + plan.vbase[ci];
+                    const uint2 *mrow = sm.u.mask + j * RB_MSTRIDE;
+                    uint16_t *lrow = sm.list + j * RB_LSTRIDE;
+                    unsigned long long M = 0ull;
+                    int q = -1;
+                    while (k < kMaxNeighbours) {
+                        bool none = false;
+                        while (M == 0ull) {
+                            if (++q >= my_rounds) {
+                                none = true;
+                                break;
+                            }
+                            const uint2 mm = mrow[q];
+                            M = (unsigned long long)mm.x | ((unsigned long long)mm.y << 32);
+                        }
+                        if (none) break;
+                        const int b = __ffsll((long long)M) - 1;
+                        M &= M - 1ull;
+                        const int slot = vm[q * 64 + b];
+                        const float4 cj = sm.rows[slot];
+                        const float dx = pi.x - cj.x, dy = pi.y - cj.y, dz = pi.z - cj.z;
+                        const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                        bool in = r2 <= c.h2_lo;
+                        if (!in && r2 < c.h2_hi) in = in_range_exact(pi.x, pi.y, pi.z, cj.x, cj.y, cj.z, c.r2_max);
+                        if (in) {
+                            lrow[k++] = (uint16_t)slot;
+                            if (slot != self) {
+                                const float d = c.h2 - r2;
+                                dens = fmaf(d * d, d, dens);
+                            }
+                        }
+                    }
+                    // a band candidate was rejected after phase 1 had stopped, or the ballot budget ran out
+                    if (k < kMaxNeighbours && my_more) walk = true;
+                }
+                // ---- results ----
+                if (in_pass) {
+                    uint8_t cflag = (uint8_t)k;
+                    if (walk) {
+                        ForceAcc dummy;
+                        dens = 0.f;
+                        const int wc = thread_walk<false>(a, g, c, t, pi, pi, 0.f, dens, dummy);
+                        cflag = (uint8_t)wc | CNT_WALK;
+                    }
+                    const float rho = dens * c.w_mass;
+                    a.srho[t] = rho;
+                    a.ncnt[t] = cflag;
+                    // per-particle pair factors ride in the .w lanes of the sorted arrays (read by the force rows)
+                    const_cast<float *>(reinterpret_cast<const float *>(a.spos + t))[3] = pressure_coeff(c, rho);
+                    const_cast<float *>(reinterpret_cast<const float *>(a.svel + t))[3] = c.lap_c / rho;
+                }
+                __syncwarp();
+                // lists: shared -> HBM, 64 B per particle, 16 B per lane and trip
+                {
+                    const int wbase = warp * 32;
+                    uint4 *gl = reinterpret_cast<uint4 *>(a.nlist + (size_t)(p0 + wbase) * 32);
+#pragma unroll
+                    for (int it = 0; it < 4; ++it) {
+                        const int row = it * 8 + (lane >> 2), part = lane & 3;   // 4 lanes x 16 B per row
+                        const int jj = wbase + row;
+                        if (jj >= j0 && jj < j1 && jj < nb) {
+                            const uint32_t *src =
+                                reinterpret_cast<const uint32_t *>(sm.list + jj * RB_LSTRIDE) + part * 4;
+                            gl[row * 4 + part] = make_uint4(src[0], src[1], src[2], src[3]);
+                        }
+                    }
+                }
+            }
+        } else if (pass >= 0) {
+            // a 32-particle pass that still does not fit: everyone walks
+            if (in_pass) {
+                ForceAcc dummy;
+                float dens = 0.f;
+                const int wc = thread_walk<false>(a, g, c, t, pi, pi, 0.f, dens, dummy);
+                const float rho = dens * c.w_mass;
+                a.srho[t] = rho;
+                a.ncnt[t] = (uint8_t)wc | CNT_WALK;
+                const_cast<float *>(reinterpret_cast<const float *>(a.spos + t))[3] = pressure_coeff(c, rho);
+                const_cast<float *>(reinterpret_cast<const float *>(a.svel + t))[3] = c.lap_c / rho;
+            }
+        }
+        if (ok && pass < 0) break;
+        ++pass;
+        if (pass * 32 >= nb) break;
+        j0 = pass * 32;
+        j1 = min(nb, j0 + 32);
+        __syncthreads();
+    }
+    if (pass == 4 && !g.aligned) {   // Q2 grid: no staging, every particle walks
+        if (live && want) {
+            ForceAcc dummy;
+            float dens = 0.f;
+            const int wc = thread_walk<false>(a, g, c, t, pi, pi, 0.f, dens, dummy);
+            a.srho[t] = dens * c.w_mass;
+            a.ncnt[t] = (uint8_t)wc | CNT_WALK;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// pressure_kernel + viscosity_kernel + integrating_kernel + collision kernel in one sweep
+// (voxel_kernels.py:135-211, base_kernels.py:30-98), driven by the slot lists of density_rows_kernel.
+// ---------------------------------------------------------------------------------------------------------------------
+template <bool RECORD>
+__global__ void __launch_bounds__(RB_THREADS, 3)
+force_rows_kernel(const SweepArgs a, const GridDesc g, const StepConsts c) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    ForceRowsSmem &sm = *reinterpret_cast<ForceRowsSmem *>(smem_raw);
+    RowPlan &plan = sm.plan;
+    const int j = threadIdx.x;
+    const int p0 = blockIdx.x * RB_THREADS;
+    const int t = p0 + j;
+    const int nb = min(RB_THREADS, a.n - p0);
+    const uint32_t key = (j < nb) ? a.skeys[t] : (uint32_t)g.ncells;
+    const bool live = key != (uint32_t)g.ncells;
+    if (j == 0) {
+        mbar_init(&plan.mbar, 1);
+        fence_mbar_init();
+    }
+    if (j < nb && !live)   // dead particle: F = external force, rho = 0 (reference NaN semantics carry on)
+        finish_particle<RECORD>(a, c, t, a.spos[t], a.svel[t], a.srho[t], ForceAcc());
+    __syncthreads();
+    if (__syncthreads_count(live) == 0) return;
+
+    int cx = 0, cy = 0, cz = 0, my_cnt = 0;
+    bool want = false, walk = false;
+    float rho_i = 0.f;
+    if (live) {
+        decode_cell(g, key, cx, cy, cz);
+        want = !(cx < g.own_lo || cx >= g.own_hi);   // x-slab: ghost cell, its owner computes the forces
+        if (want) {
+            const uint8_t cf = a.ncnt[t];
+            walk = (cf & CNT_WALK) != 0;
+            my_cnt = walk ? 0 : cf;
+            rho_i = a.srho[t];
+        }
+    }
+
+    uint32_t parity = 0;
+    int pass = g.aligned ? -1 : 4;
+    int j0 = 0, j1 = nb;
+    while (pass < 4) {
+        int ci = 0;
+        const bool ok = rows_setup<false>(a, g, plan, sm.rpos, sm.rvel, nullptr, j0, j1, t, key, live, ci);
+        const bool in_pass = live && want && j >= j0 && j < j1;
+        if (ok) {
+            // the lists travel while the rows land
+            uint4 e[4];
+            const uint4 *lg = reinterpret_cast<const uint4 *>(a.nlist + (size_t)t * 32);
+            if (in_pass && !walk) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (q * 8 < my_cnt) e[q] = __ldg(&lg[q]);
+            }
+            while (!mbar_try_wait(&plan.mbar, parity)) {
+            }
+            parity ^= 1u;
+            if (in_pass) {
+                float4 pi, vi;
+                ForceAcc f;
+                if (!walk) {
+                    const int self = plan.slot13[ci] + (t - plan.start13[ci]);
+                    pi = sm.rpos[self];
+                    vi = sm.rvel[self];
+                    const float a_i = pi.w;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        if (q * 8 < my_cnt) {
+                            const uint32_t w[4] = {e[q].x, e[q].y, e[q].z, e[q].w};
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) {
+                                const int raw = (int)((w[u >> 1] >> ((u & 1) * 16)) & 0xffffu);
+                                const int slot = (q * 8 + u < my_cnt) ? raw : self;
+                                f.pair(c, pi, vi, a_i, sm.rpos[slot], sm.rvel[slot], slot != self);
+                            }
+                        }
+                    }
+                } else {
+                    pi = a.spos[t];
+                    vi = a.svel[t];
+                    float dens = 0.f;
+                    thread_walk<true>(a, g, c, t, pi, vi, pressure_coeff(c, rho_i), dens, f);
+                }
+                finish_particle<RECORD>(a, c, t, pi, vi, rho_i, f);
+            }
+        } else if (pass >= 0) {
+            if (in_pass) {
+                const float4 pi = a.spos[t], vi = a.svel[t];
+                ForceAcc f;
+                float dens = 0.f;
+                thread_walk<true>(a, g, c, t, pi, vi, pressure_coeff(c, rho_i), dens, f);
+                finish_particle<RECORD>(a, c, t, pi, vi, rho_i, f);
+            }
+        }
+        if (ok && pass < 0) break;
+        ++pass;
+        if (pass * 32 >= nb) break;
+        j0 = pass * 32;
+        j1 = min(nb, j0 + 32);
+        __syncthreads();
+    }
+    if (pass == 4 && !g.aligned) {
+        if (live && want) {
+            const float4 pi = a.spos[t], vi = a.svel[t];
+            ForceAcc f;
+            float dens = 0.f;
+            thread_walk<true>(a, g, c, t, pi, vi, pressure_coeff(c, rho_i), dens, f);
+            finish_particle<RECORD>(a, c, t, pi, vi, rho_i, f);
+        }
+    }
+}
+
+}  // namespace sph
