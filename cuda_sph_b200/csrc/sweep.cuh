@@ -124,10 +124,10 @@ __device__ __noinline__ void finish_particle(const SweepArgs &a, const StepConst
                    c.ext[2] + -(double)f.pz + (double)f.uz};
     double v[3] = {vi.x, vi.y, vi.z};
     double x[3] = {pi.x, pi.y, pi.z};
-    const double rho_d = (double)rho_i;
+    const double s_dt = c.dt / (double)rho_i;   // F / rho * dt with one division (rho = 0 keeps the inf / NaN semantics)
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
-        v[d] += F[d] / rho_d * c.dt;
+        v[d] += F[d] * s_dt;
         x[d] += v[d] * c.dt;
     }
     const uint32_t id = a.sids[t];

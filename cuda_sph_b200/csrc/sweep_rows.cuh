@@ -7,26 +7,25 @@
 // their cells lie in 9 contiguous ranges of the sorted arrays ("rows": one per (dy, dz), covering the x-neighbours).
 //
 // One CTA = 128 consecutive sorted particles:
-//   setup   find the CTA's non-empty cells, fetch their 27 cell ranges, take per-row min/max -> 9 row ranges; ONE
-//           THREAD issues 9 (density) / 18 (force) 1-D TMA bulk copies (cp.async.bulk -> UBLKCP) that land the rows in
-//           shared memory and signal an mbarrier; meanwhile the warps build, per cell, the map from the cell's
-//           candidate sequence ("virtual list") to row slots (`vmap`, 2 B per candidate).
-//   density phase 1 (warp-cooperative, one particle at a time): the 32 lanes test 64 candidates per round straight
-//           from the staged rows and keep only the two ballots; a particle stops after the round in which it reaches
-//           32 hits -- nobody idles behind a slower neighbour and no lane is lost at low particles-per-cell.  The test
-//           is the fp32 superset r2 < h^2 (1 + 1e-5).
-//   density phase 2 (lane = particle): walks its own ballots in order, re-evaluates the accepted candidates (fp64
-//           predicate inside the rounding band -> neighbour lists are bit-identical to the fp64 reference), writes the
-//           list of row SLOTS, accumulates the poly6 density, and publishes rho, the count, the list and the
-//           per-particle factors p/rho^2 and LAP_W_CONST/rho (into the .w lanes of the sorted position / velocity).
+//   setup   find the CTA's non-empty cells, fetch their 27 cell ranges, take per-row min/max -> 9 row ranges; warp 0
+//           issues 9 (density) / 18 (force) 1-D TMA bulk copies (cp.async.bulk -> UBLKCP) that land the rows in shared
+//           memory and signal an mbarrier; the per-cell segment tables are turned into row slots meanwhile.
+//   density lane = particle.  Each lane walks the 27 segments of its cell in reference order straight over the staged
+//           rows (LDS.128 per candidate, software-prefetched) and keeps the first 32 candidates of the fp32 superset
+//           r2 < h^2 (1 + 1e-5); a second, short pass over the kept candidates applies the fp64 predicate inside the
+//           rounding band (so neighbour lists are bit-identical to the fp64 reference) and accumulates the poly6
+//           density in list order.  Consecutive sorted particles share cells, so the lanes of a warp read the same
+//           candidate most of the time (shared-memory broadcast) and all 32 lanes are busy at any particles-per-cell.
+//           Outputs: rho, neighbour count, the list of row SLOTS, and the per-particle pair factors p/rho^2 and
+//           LAP_W_CONST/rho (into the .w lanes of the sorted position / velocity, picked up by the force rows).
 //   force   same setup (positions + velocities), then lane = particle runs down its slot list: 2 LDS.128 + ~40 FP
 //           instructions per pair, no reductions, list order == the reference's summation order; fp64 integrate +
 //           collide epilogue and scatter to the id-ordered master arrays (finish_particle, sweep.cuh).
 // Both kernels derive the row layout from (sorted keys, cell table) with the same code, so a slot means the same thing
 // in both.  A CTA whose rows do not fit shared memory falls back to four 32-particle passes; a pass that still does
 // not fit, particles whose own cell differs from their sort cell (aliased keys, reference quirk Q5), grids whose
-// trunc and ceil dims differ (Q2) and particles that exhaust their ballot budget take the plain one-thread walk of
-// sweep.cuh (exact, slow, rare).
+// trunc and ceil dims differ (Q2) and particles with a rejected band candidate take the plain one-thread walk of
+// sweep.cuh over global memory (exact, slow, rare).
 #pragma once
 #include "sweep.cuh"
 
@@ -36,10 +35,8 @@ constexpr int RB_THREADS = 128;   // threads == particles per CTA
 constexpr int RB_WARPS = RB_THREADS / 32;
 constexpr int RB_CAP = 2048;      // row slots per CTA pass (candidates staged in shared memory)
 constexpr int RB_MAXC = 64;       // non-empty cells per CTA pass
-constexpr int RB_VCAP = 6144;     // vmap entries per CTA pass
-constexpr int RB_MR = 12;         // ballot rounds (64 candidates each) kept per particle
-constexpr int RB_MSTRIDE = 13;    // uint2 per ballot row (26 words: conflict-free LDS.64 per half warp)
-constexpr int RB_LSTRIDE = 34;    // uint16 per list row (17 words: conflict-free rows)
+constexpr int RB_KEEP = 33;       // superset candidates kept per particle (32 + spares for rejected band candidates)
+constexpr int RB_LSTRIDE = 38;    // uint16 per list row (19 words: conflict-free rows; >= RB_KEEP + 1)
 
 // ---- mbarrier + 1-D TMA bulk copy -----------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -84,27 +81,20 @@ struct RowPlan {
     uint32_t ckey[RB_MAXC];     // key of local cell ci
     int start13[RB_MAXC];       // sorted index of the first particle of the cell
     int slot13[RB_MAXC];        // its row slot
-    int vbase[RB_MAXC];         // first vmap entry of the cell            (density only)
-    int Tc[RB_MAXC];            // length of the cell's virtual list        (density only)
 };
 
 struct DensityRowsSmem {
-    float4 rows[RB_CAP + 1];                        // [RB_CAP] = far-away sentinel candidate
-    uint16_t vmap[RB_VCAP];
-    union {
-        uint2 mask[RB_THREADS * RB_MSTRIDE];        // phase 1 -> phase 2 ballots
-        struct {                                    // setup only (dead before phase 1)
-            int seg_start[RB_MAXC * 27];
-            uint16_t seg_off[RB_MAXC * 28];
-        } t;
-    } u;
+    float4 rows[RB_CAP + 8];                 // [RB_CAP..] = far-away sentinel candidates (prefetch may touch them)
+    // per local cell, its 27 segments in walk order: setup writes the sorted start (int), then slot | count << 16
+    uint32_t seg[RB_MAXC * 27];
+    uint16_t seg_cnt[RB_MAXC * 27];
     uint16_t list[RB_THREADS * RB_LSTRIDE];
     RowPlan plan;
 };
 
 struct ForceRowsSmem {
-    float4 rpos[RB_CAP + 1];   // (x, y, z, p/rho^2)
-    float4 rvel[RB_CAP + 1];   // (vx, vy, vz, LAP_W_CONST/rho)
+    float4 rpos[RB_CAP + 2];   // (x, y, z, p/rho^2)
+    float4 rvel[RB_CAP + 2];   // (vx, vy, vz, LAP_W_CONST/rho)
     RowPlan plan;
 };
 
@@ -165,21 +155,14 @@ __device__ __forceinline__ bool rows_setup(const SweepArgs &a, const GridDesc &g
             atomicMax(&plan.row_hi[lane % 9], r.y);
         }
         if (lane == 13) plan.start13[c] = r.x;
-        if (DENSITY) {
-            int inc = cnt;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int u = __shfl_up_sync(FULL, inc, o);
-                if (lane >= o) inc += u;
-            }
-            if (lane < 27) ds->u.t.seg_start[c * 27 + lane] = r.x;
-            if (lane < 28) ds->u.t.seg_off[c * 28 + lane] = (uint16_t)min(inc - cnt, 65535);   // [27] = T (saturated)
-            if (lane == 31) plan.Tc[c] = inc;
+        if (DENSITY && lane < 27) {
+            ds->seg[c * 27 + lane] = (uint32_t)r.x;
+            ds->seg_cnt[c * 27 + lane] = (uint16_t)min(cnt, 65535);
         }
     }
     __syncthreads();
 
-    // ---- row bases, vmap bases, capacity check, TMA issue (warp 0) ----
+    // ---- row bases, capacity check, TMA issue (warp 0) ----
     if (warp == 0) {
         const int len = (lane < 9) ? max(plan.row_hi[lane] - plan.row_lo[lane], 0) : 0;
         int inc = len;
@@ -190,23 +173,7 @@ __device__ __forceinline__ bool rows_setup(const SweepArgs &a, const GridDesc &g
         }
         const int slots = __shfl_sync(FULL, inc, 8);
         if (lane < 9) plan.row_base[lane] = inc - len;
-        bool fits = slots <= RB_CAP;
-        if (DENSITY) {
-            int vtot = 0;
-            for (int base = 0; base < total; base += 32) {
-                const int c = base + lane;
-                const int vlen = (c < total) ? min((plan.Tc[c] + 63) & ~63, RB_MR * 64) : 0;
-                int vi = vlen;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int u = __shfl_up_sync(FULL, vi, o);
-                    if (lane >= o) vi += u;
-                }
-                if (c < total) plan.vbase[c] = vtot + vi - vlen;
-                vtot += __shfl_sync(FULL, vi, 31);
-            }
-            fits = fits && vtot <= RB_VCAP;
-        }
+        const bool fits = slots <= RB_CAP;
         if (lane == 0) {
             plan.row_base[9] = slots;
             plan.ncell = total;
@@ -227,28 +194,28 @@ __device__ __forceinline__ bool rows_setup(const SweepArgs &a, const GridDesc &g
     __syncthreads();
     if (!plan.fits) return false;
 
-    // ---- per cell: slot of the own segment; density: virtual list -> slot map ----
+    // ---- per cell: slot of the own segment; density: sorted starts -> row slots ----
     for (int c = warp; c < total; c += RB_WARPS) {
         if (DENSITY) {
-            const int vb = plan.vbase[c], T = plan.Tc[c];
-            const int vlen = min((T + 63) & ~63, RB_MR * 64);
             if (lane < 27) {
-                const int off0 = ds->u.t.seg_off[c * 28 + lane];
-                const int cnt = (int)ds->u.t.seg_off[c * 28 + lane + 1] - off0;
-                const int start = ds->u.t.seg_start[c * 27 + lane];
+                const int start = (int)ds->seg[c * 27 + lane];
+                const int cnt = ds->seg_cnt[c * 27 + lane];
                 const int slot0 = plan.row_base[lane % 9] + (start - plan.row_lo[lane % 9]);
+                ds->seg[c * 27 + lane] = cnt ? ((uint32_t)slot0 | ((uint32_t)cnt << 16)) : 0u;
                 if (lane == 13) plan.slot13[c] = slot0;
-                uint16_t *dst = ds->vmap + vb + off0;
-                const int m = min(cnt, vlen - off0);
-                for (int l = 0; l < m; ++l) dst[l] = (uint16_t)(slot0 + l);
             }
-            for (int v = T + lane; v < vlen; v += 32) ds->vmap[vb + v] = (uint16_t)RB_CAP;
         } else if (lane == 0) {
             plan.slot13[c] = plan.row_base[4] + (plan.start13[c] - plan.row_lo[4]);
         }
     }
     __syncthreads();
     return true;
+}
+
+// lk + 2 if r < lim else lk: one FSETP + one predicated add (the list offset advances only on a hit)
+__device__ __forceinline__ int advance_if_less(int lk, float r, float lim) {
+    asm("{\n\t.reg .pred p;\n\tsetp.lt.f32 p, %1, %2;\n\t@p add.s32 %0, %0, 2;\n\t}" : "+r"(lk) : "f"(r), "f"(lim));
+    return lk;
 }
 
 // Does the particle's own cell (from its position, fp64 division + C truncation: voxel_kernels.py:40-41) equal the
@@ -265,7 +232,17 @@ __device__ __forceinline__ bool own_cell_matches(const GridDesc &g, const float4
 // ---------------------------------------------------------------------------------------------------------------------
 // density_kernel (voxel_kernels.py:108-132) + neighbour lists
 // ---------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(RB_THREADS, 3)
+__device__ __forceinline__ void publish_density(const SweepArgs &a, const StepConsts &c, int t, float dens,
+                                                uint8_t cflag) {
+    const float rho = dens * c.w_mass;
+    a.srho[t] = rho;
+    a.ncnt[t] = cflag;
+    // per-particle pair factors ride in the .w lanes of the sorted arrays (read by the force rows)
+    const_cast<float *>(reinterpret_cast<const float *>(a.spos + t))[3] = pressure_coeff(c, rho);
+    const_cast<float *>(reinterpret_cast<const float *>(a.svel + t))[3] = c.lap_c / rho;
+}
+
+__global__ void __launch_bounds__(RB_THREADS, 4)
 density_rows_kernel(const SweepArgs a, const GridDesc g, const StepConsts c) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     DensityRowsSmem &sm = *reinterpret_cast<DensityRowsSmem *>(smem_raw);
@@ -279,8 +256,8 @@ density_rows_kernel(const SweepArgs a, const GridDesc g, const StepConsts c) {
     if (j == 0) {
         mbar_init(&plan.mbar, 1);
         fence_mbar_init();
-        sm.rows[RB_CAP] = make_float4(1e18f, 1e18f, 1e18f, 0.f);
     }
+    if (j < 8) sm.rows[RB_CAP + j] = make_float4(1e18f, 1e18f, 1e18f, 0.f);
     if (j < nb && !live) {   // dead particle: no neighbours
         a.srho[t] = 0.f;
         a.ncnt[t] = 0;
@@ -311,111 +288,105 @@ density_rows_kernel(const SweepArgs a, const GridDesc g, const StepConsts c) {
             }
             parity ^= 1u;
             const bool active = in_pass && !walk;
-            const int self = active ? plan.slot13[ci] + (t - plan.start13[ci]) : 0;
-            int my_rounds = 0;
-            bool my_more = false;   // phase 1 stopped before the end of the virtual list
-            const bool warp_in = (warp * 32 < j1) && (warp * 32 + 32 > j0);
-            if (warp_in) {
-                // ---- phase 1: one particle at a time, 32 lanes x 2 candidates per round, ballots only ----
-                unsigned todo = __ballot_sync(FULL, active);
-                while (todo) {
-                    const int il = __ffs(todo) - 1;
-                    todo &= todo - 1;
-                    const int cil = __shfl_sync(FULL, ci, il);
-                    const int sslot = __shfl_sync(FULL, self, il);
-                    const int T = plan.Tc[cil];
-                    const int nr = min((T + 63) >> 6, RB_MR);
-                    const float4 p = sm.rows[sslot];
-                    const uint16_t *vm = sm.vmap + plan.vbase[cil] + lane;
-                    uint2 *mrow = sm.u.mask + (warp * 32 + il) * RB_MSTRIDE;
-                    int cnt = 0, q = 0;
-                    for (; q < nr;) {
-                        const float4 c0 = sm.rows[vm[q * 64]], c1 = sm.rows[vm[q * 64 + 32]];
-                        const float dx0 = p.x - c0.x, dy0 = p.y - c0.y, dz0 = p.z - c0.z;
-                        const float dx1 = p.x - c1.x, dy1 = p.y - c1.y, dz1 = p.z - c1.z;
-                        const float r0 = fmaf(dz0, dz0, fmaf(dy0, dy0, dx0 * dx0));
-                        const float r1 = fmaf(dz1, dz1, fmaf(dy1, dy1, dx1 * dx1));
-                        const unsigned m0 = __ballot_sync(FULL, r0 < c.h2_hi), m1 = __ballot_sync(FULL, r1 < c.h2_hi);
-                        if (lane == 0) mrow[q] = make_uint2(m0, m1);
-                        cnt += __popc(m0) + __popc(m1);
-                        ++q;
-                        if (cnt >= kMaxNeighbours) break;
+            if (active) {
+                // lane = particle, in sorted order: the lanes of a warp share one or two cells, hence read the same
+                // candidate most of the time (broadcast).  (Regrouping the CTA's particles by fractional x, which
+                // governs the scan length, was measured slower: lanes of different cells diverge at every segment.)
+                const int jj = j;
+                const int tj = t;
+                const int selfj = plan.slot13[ci] + (t - plan.start13[ci]);
+                const float4 pj = pi;
+                uint16_t *const lrow = sm.list + jj * RB_LSTRIDE;
+                // ---- scan: walk the cell's 27 segments in reference order over the staged rows, keep the first
+                //      RB_KEEP candidates of the fp32 superset r2 < h^2 (1 + 1e-5); two candidates per trip ----
+                // next free entry of the list row, as a BYTE offset into sm.list: every candidate is stored, the offset
+                // only advances on a hit (one STS + one predicated add per candidate)
+                char *const lbytes = reinterpret_cast<char *>(sm.list);
+                int lk = jj * RB_LSTRIDE * 2;
+                const int lend = lk + RB_KEEP * 2;
+                const uint32_t *seg = sm.seg + ci * 27;
+                for (int s = 0; s < 27 && lk < lend; ++s) {
+                    const uint32_t e = seg[s];
+                    int slot = (int)(e & 0xffffu);
+                    int n = (int)(e >> 16);
+                    // four candidates per trip, double-buffered: (a0, a1) were loaded one trip ahead, (b0, b1) are
+                    // loaded at the top of the trip they are used in -- LDS latency hides behind the other pair's math
+                    float4 a0 = sm.rows[slot], a1 = sm.rows[slot + 1];
+#define SPH_TEST_CANDIDATE(cand, sl)                                                        \
+    {                                                                                       \
+        const float dx_ = pj.x - (cand).x, dy_ = pj.y - (cand).y, dz_ = pj.z - (cand).z;    \
+        const float r_ = fmaf(dz_, dz_, fmaf(dy_, dy_, dx_ * dx_));                         \
+        *reinterpret_cast<uint16_t *>(lbytes + lk) = (uint16_t)(sl);                        \
+        lk = advance_if_less(lk, r_, c.h2_hi);                                              \
+    }
+                    while (n >= 4) {
+                        const float4 b0 = sm.rows[slot + 2], b1 = sm.rows[slot + 3];
+                        SPH_TEST_CANDIDATE(a0, slot)
+                        SPH_TEST_CANDIDATE(a1, slot + 1)
+                        a0 = sm.rows[slot + 4];   // next trip (at worst sentinels)
+                        a1 = sm.rows[slot + 5];
+                        SPH_TEST_CANDIDATE(b0, slot + 2)
+                        SPH_TEST_CANDIDATE(b1, slot + 3)
+                        slot += 4;
+                        n -= 4;
+                        if (lk >= lend) break;
                     }
-                    if (lane == il) {
-                        my_rounds = q;
-                        my_more = q * 64 < T;
+                    if (n >= 2 && n < 4 && lk < lend) {
+                        const float4 b0 = sm.rows[slot + 2];
+                        SPH_TEST_CANDIDATE(a0, slot)
+                        SPH_TEST_CANDIDATE(a1, slot + 1)
+                        a0 = b0;
+                        slot += 2;
+                        n -= 2;
                     }
+                    if (n == 1 && lk < lend) SPH_TEST_CANDIDATE(a0, slot)
+#undef SPH_TEST_CANDIDATE
                 }
-                __syncwarp();
-                // ---- phase 2: lane = particle, ballots -> exact list + density ----
+                const int kept = (lk >> 1) - jj * RB_LSTRIDE;   // <= RB_KEEP + 1
+                // ---- exact pass: fp64 predicate inside the rounding band, first 32 accepted stay (compacted in place),
+                //      poly6 density in list order ----
                 int k = 0;
                 float dens = 0.f;
-                if (active) {
-                    const uint16_t *vm = sm.vmap + plan.vbase[ci];
-                    const uint2 *mrow = sm.u.mask + j * RB_MSTRIDE;
-                    uint16_t *lrow = sm.list + j * RB_LSTRIDE;
-                    unsigned long long M = 0ull;
-                    int q = -1;
-                    while (k < kMaxNeighbours) {
-                        bool none = false;
-                        while (M == 0ull) {
-                            if (++q >= my_rounds) {
-                                none = true;
-                                break;
-                            }
-                            const uint2 mm = mrow[q];
-                            M = (unsigned long long)mm.x | ((unsigned long long)mm.y << 32);
-                        }
-                        if (none) break;
-                        const int b = __ffsll((long long)M) - 1;
-                        M &= M - 1ull;
-                        const int slot = vm[q * 64 + b];
-                        const float4 cj = sm.rows[slot];
-                        const float dx = pi.x - cj.x, dy = pi.y - cj.y, dz = pi.z - cj.z;
-                        const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-                        bool in = r2 <= c.h2_lo;
-                        if (!in && r2 < c.h2_hi) in = in_range_exact(pi.x, pi.y, pi.z, cj.x, cj.y, cj.z, c.r2_max);
-                        if (in) {
-                            lrow[k++] = (uint16_t)slot;
-                            if (slot != self) {
-                                const float d = c.h2 - r2;
-                                dens = fmaf(d * d, d, dens);
-                            }
-                        }
+                for (int i = 0; i < kept && k < kMaxNeighbours; ++i) {
+                    const int slot = lrow[i];
+                    const float4 cj = sm.rows[slot];
+                    const float dx = pj.x - cj.x, dy = pj.y - cj.y, dz = pj.z - cj.z;
+                    const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                    if (r2 > c.h2_lo && !in_range_exact(pj.x, pj.y, pj.z, cj.x, cj.y, cj.z, c.r2_max)) continue;
+                    lrow[k++] = (uint16_t)slot;
+                    if (slot != selfj) {
+                        const float d = c.h2 - r2;
+                        dens = fmaf(d * d, d, dens);
                     }
-                    // a band candidate was rejected after phase 1 had stopped, or the ballot budget ran out
-                    if (k < kMaxNeighbours && my_more) walk = true;
                 }
-                // ---- results ----
-                if (in_pass) {
-                    uint8_t cflag = (uint8_t)k;
-                    if (walk) {
-                        ForceAcc dummy;
-                        dens = 0.f;
-                        const int wc = thread_walk<false>(a, g, c, t, pi, pi, 0.f, dens, dummy);
-                        cflag = (uint8_t)wc | CNT_WALK;
-                    }
-                    const float rho = dens * c.w_mass;
-                    a.srho[t] = rho;
-                    a.ncnt[t] = cflag;
-                    // per-particle pair factors ride in the .w lanes of the sorted arrays (read by the force rows)
-                    const_cast<float *>(reinterpret_cast<const float *>(a.spos + t))[3] = pressure_coeff(c, rho);
-                    const_cast<float *>(reinterpret_cast<const float *>(a.svel + t))[3] = c.lap_c / rho;
+                uint8_t cflag = (uint8_t)k;
+                if (k < kMaxNeighbours && kept >= RB_KEEP) {
+                    // the scan stopped on its budget and too many band candidates were rejected: redo exactly
+                    ForceAcc dummy;
+                    dens = 0.f;
+                    const int wc = thread_walk<false>(a, g, c, tj, pj, pj, 0.f, dens, dummy);
+                    cflag = (uint8_t)wc | CNT_WALK;
                 }
-                __syncwarp();
-                // lists: shared -> HBM, 64 B per particle, 16 B per lane and trip
-                {
-                    const int wbase = warp * 32;
-                    uint4 *gl = reinterpret_cast<uint4 *>(a.nlist + (size_t)(p0 + wbase) * 32);
+                publish_density(a, c, tj, dens, cflag);
+            }
+            if (in_pass && walk) {   // aliased key (quirk Q5): plain walk by the particle's own thread
+                ForceAcc dummy;
+                float dens = 0.f;
+                const int wc = thread_walk<false>(a, g, c, t, pi, pi, 0.f, dens, dummy);
+                publish_density(a, c, t, dens, (uint8_t)wc | CNT_WALK);
+            }
+            __syncwarp();
+            // lists: shared -> HBM, 64 B per particle, 16 B per lane and trip (rows of this warp's own particles)
+            {
+                const int wbase = warp * 32;
+                uint4 *gl = reinterpret_cast<uint4 *>(a.nlist + (size_t)(p0 + wbase) * 32);
 #pragma unroll
-                    for (int it = 0; it < 4; ++it) {
-                        const int row = it * 8 + (lane >> 2), part = lane & 3;   // 4 lanes x 16 B per row
-                        const int jj = wbase + row;
-                        if (jj >= j0 && jj < j1 && jj < nb) {
-                            const uint32_t *src =
-                                reinterpret_cast<const uint32_t *>(sm.list + jj * RB_LSTRIDE) + part * 4;
-                            gl[row * 4 + part] = make_uint4(src[0], src[1], src[2], src[3]);
-                        }
+                for (int it = 0; it < 4; ++it) {
+                    const int row = it * 8 + (lane >> 2), part = lane & 3;   // 4 lanes x 16 B per row
+                    const int jj = wbase + row;
+                    if (jj >= j0 && jj < j1 && jj < nb) {
+                        const uint32_t *src = reinterpret_cast<const uint32_t *>(sm.list + jj * RB_LSTRIDE) + part * 4;
+                        gl[row * 4 + part] = make_uint4(src[0], src[1], src[2], src[3]);
                     }
                 }
             }
@@ -425,11 +396,7 @@ density_rows_kernel(const SweepArgs a, const GridDesc g, const StepConsts c) {
                 ForceAcc dummy;
                 float dens = 0.f;
                 const int wc = thread_walk<false>(a, g, c, t, pi, pi, 0.f, dens, dummy);
-                const float rho = dens * c.w_mass;
-                a.srho[t] = rho;
-                a.ncnt[t] = (uint8_t)wc | CNT_WALK;
-                const_cast<float *>(reinterpret_cast<const float *>(a.spos + t))[3] = pressure_coeff(c, rho);
-                const_cast<float *>(reinterpret_cast<const float *>(a.svel + t))[3] = c.lap_c / rho;
+                publish_density(a, c, t, dens, (uint8_t)wc | CNT_WALK);
             }
         }
         if (ok && pass < 0) break;
@@ -444,8 +411,7 @@ density_rows_kernel(const SweepArgs a, const GridDesc g, const StepConsts c) {
             ForceAcc dummy;
             float dens = 0.f;
             const int wc = thread_walk<false>(a, g, c, t, pi, pi, 0.f, dens, dummy);
-            a.srho[t] = dens * c.w_mass;
-            a.ncnt[t] = (uint8_t)wc | CNT_WALK;
+            publish_density(a, c, t, dens, (uint8_t)wc | CNT_WALK);
         }
     }
 }
