@@ -49,8 +49,9 @@ BYTES = {"hash": 20, "reorder": 72, "density": 20, "force": 84}
 
 
 def sort_bytes(passes: int) -> int:
-    # per pass: hist reads the key (4), scatter reads key+value (8) and writes key+value (8); pass 0 has no value read
-    return passes * 20 - 4
+    # onesweep: one histogram pass reads the keys (4); every digit pass reads key + value (8) and writes key + value
+    # (8); pass 0 has no value read (values are iota)
+    return 4 + passes * 16 - 4
 
 
 def make_workload(name: str, n_override: int | None):
@@ -305,7 +306,7 @@ def run_gpu_arm(args):
         t = s.step_timed(1)
         for k_, v_ in t.items():
             acc[k_] = acc.get(k_, 0.0) + v_
-    passes = (t["launches_per_step"] - 5) // 3
+    passes = t["sort_passes"]
     hbm_peak, peak_src = peaks()
     stage_ms = {k_: acc[k_ + "_ms"] / KT for k_ in ("hash", "sort", "reorder", "density", "force")}
     stage_bytes = dict(BYTES, sort=sort_bytes(passes))

@@ -23,7 +23,7 @@ class SphParams(C.Structure):
 class SphTimings(C.Structure):
     _fields_ = [("hash_ms", C.c_float), ("sort_ms", C.c_float), ("reorder_ms", C.c_float),
                 ("density_ms", C.c_float), ("force_ms", C.c_float), ("total_ms", C.c_float), ("steps", C.c_int32),
-                ("launches_per_step", C.c_int32)]
+                ("launches_per_step", C.c_int32), ("sort_passes", C.c_int32)]
 
 
 class SphStats(C.Structure):

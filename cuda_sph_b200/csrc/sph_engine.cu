@@ -3,6 +3,7 @@
 // Step pipeline (device resident, replayed as a CUDA graph):
 //   hash_kernel -> [rs_hist, rs_scan, rs_scatter] x passes -> memset(cell_range) -> reorder_kernel
 //   -> density_kernel -> force_kernel (pressure + viscosity + integrate + collide, scatter to master)
+#include <algorithm>
 #include <climits>
 #include <cmath>
 #include <cstdio>
@@ -12,6 +13,7 @@
 #include <vector>
 
 #include "../../include/sph_b200.h"
+#include "radix_onesweep.cuh"
 #include "radix_sort.cuh"
 #include "sph_kernels.cuh"
 #include "sweep.cuh"
@@ -52,6 +54,8 @@ struct SphEngine {
     uint32_t *keys = nullptr, *ka = nullptr, *va = nullptr, *kb = nullptr, *vb = nullptr;
     uint32_t *skeys = nullptr, *sids = nullptr;  // aliases of the final sort buffers
     uint32_t *block_hist = nullptr, *digit_total = nullptr;
+    uint32_t *os_ctrl = nullptr;      // onesweep control block (histograms, tickets, look-back status)
+    bool onesweep = true;         // SPH_SORT=classic selects the three-kernel passes of radix_sort.cuh
     int ntiles = 0, passes = 0, pass_bits[8]{}, key_bits = 0;
     int2 *cell_range = nullptr;
     // pipe
@@ -263,6 +267,9 @@ int sph_create(const SphParams *params, int device, sph_handle_t *out) {
     ALLOC(e->vb, n);
     ALLOC(e->block_hist, (size_t)RS_RADIX * e->ntiles);
     ALLOC(e->digit_total, RS_RADIX);
+    if (const char *so = getenv("SPH_SORT")) e->onesweep = strcmp(so, "classic") != 0;
+    if (e->passes > OS_MAX_PASSES) e->onesweep = false;
+    ALLOC(e->os_ctrl, os_ctrl_words(e->passes, (n + OS_TILE - 1) / OS_TILE));
     ALLOC(e->cell_range, e->cell_capacity);
     if (e->slab) ALLOC(e->gid, n);
     ALLOC(e->stats_d, 4);
@@ -305,7 +312,7 @@ int sph_create(const SphParams *params, int device, sph_handle_t *out) {
                          (int)sizeof(ForceRowsSmem));
     cudaFuncSetAttribute(force_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)sizeof(ForceRowsSmem));
-    e->launches_per_step = 1 + 3 * e->passes + 1 + 1 + 1 + 1;
+    e->launches_per_step = 1 + (e->onesweep ? 2 + e->passes : 3 * e->passes) + 1 + 1 + 1 + 1;
     if (cudaDeviceSynchronize() != cudaSuccess) {
         sph_destroy(e);
         return fail("device error during create");
@@ -320,7 +327,7 @@ int sph_destroy(sph_handle_t e) {
     cudaDeviceSynchronize();
     invalidate_graph(e);
     void *ptrs[] = {e->pos_m, e->vel_m, e->spos, e->svel, e->sforce, e->spress, e->svisc, e->srho, e->nlist, e->ncnt,
-                    e->keys, e->ka, e->va, e->kb, e->vb, e->block_hist, e->digit_total, e->cell_range, e->pipe_d,
+                    e->keys, e->ka, e->va, e->kb, e->vb, e->block_hist, e->digit_total, e->os_ctrl, e->cell_range, e->pipe_d,
                     e->rng, e->gid, e->stage, e->stats_d, e->snap_pos, e->snap_vel, e->snap_rng};
     for (void *q : ptrs)
         if (q) cudaFree(q);
@@ -406,7 +413,28 @@ static int enqueue_step(SphEngine *e, bool timed, int n, int n_own) {
     hash_kernel<<<g256, 256, 0, s>>>(e->pos_m, e->keys, n, e->grid);
     if (timed) cudaEventRecord(e->ev[1], s);
     // LSD radix sort of (key, id): pass 0 reads keys with implicit iota values
-    {
+    if (e->onesweep) {
+        const int otiles = (n + OS_TILE - 1) / OS_TILE;
+        OsPasses ps{};
+        ps.n_passes = e->passes;
+        int shift = 0;
+        for (int p = 0; p < e->passes; ++p) {
+            ps.shift[p] = shift;
+            ps.mask[p] = (1u << e->pass_bits[p]) - 1u;
+            shift += e->pass_bits[p];
+        }
+        cudaMemsetAsync(e->os_ctrl, 0, sizeof(uint32_t) * os_ctrl_words(e->passes, otiles), s);
+        os_hist<<<std::min(otiles, 148 * 8), OS_THREADS, 0, s>>>(e->keys, n, ps, e->os_ctrl);
+        const uint32_t *kin = e->keys, *vin = nullptr;
+        for (int p = 0; p < e->passes; ++p) {
+            uint32_t *kout = (p % 2 == 0) ? e->ka : e->kb;
+            uint32_t *vout = (p % 2 == 0) ? e->va : e->vb;
+            os_pass<<<otiles, OS_THREADS, 0, s>>>(kin, vin, kout, vout, n, p, e->passes, ps.shift[p], ps.mask[p], otiles,
+                                                  e->os_ctrl);
+            kin = kout;
+            vin = vout;
+        }
+    } else {
         const uint32_t *kin = e->keys, *vin = nullptr;
         int shift = 0;
         for (int p = 0; p < e->passes; ++p) {
@@ -529,6 +557,7 @@ int sph_step_timed(sph_handle_t e, int32_t n_steps, SphTimings *t) {
     }
     t->steps = n_steps;
     t->launches_per_step = e->launches_per_step;
+    t->sort_passes = e->passes;
     e->steps_done += n_steps;
     e->launches += (int64_t)n_steps * e->launches_per_step;
     return 0;

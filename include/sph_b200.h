@@ -68,6 +68,7 @@ typedef struct SphTimings {
     float total_ms;
     int32_t steps;
     int32_t launches_per_step; /* kernels + memsets this library launches per step */
+    int32_t sort_passes;       /* 8-bit digit passes of the radix sort (ceil(log2(n_cells + 1)) bits)  */
 } SphTimings;
 
 typedef struct SphStats {
