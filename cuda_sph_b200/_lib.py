@@ -54,6 +54,13 @@ EXPORTS = {
     "sph_restore_state": (C.c_int, [_H]),
     "sph_slab_configure": (C.c_int, [_H, C.c_int32, C.c_int32, C.c_int64]),
     "sph_slab_step": (C.c_int, [_H, C.c_int32, C.c_int32]),
+    "sph_slab_exchange_init": (C.c_int, [_H, C.c_int32, C.c_int32, _P, C.c_int32, _P, _P, C.POINTER(C.c_void_p),
+                                         C.POINTER(C.c_void_p), _P]),
+    "sph_slab_route": (C.c_int, [_H]),
+    "sph_slab_unpack": (C.c_int, [_H]),
+    "sph_slab_step_all": (C.c_int, [_H]),
+    "sph_slab_compact": (C.c_int, [_H]),
+    "sph_slab_counters": (C.c_int, [_H, _P]),
     "sph_get_keys": (C.c_int, [_H, _P]),
     "sph_get_sorted_ids": (C.c_int, [_H, _P]),
     "sph_get_sorted_keys": (C.c_int, [_H, _P]),

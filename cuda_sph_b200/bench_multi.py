@@ -15,7 +15,7 @@ import torch.distributed as dist
 
 def run(args, rank, world, local_rank):
     import bench
-    from .slab import GpuSlabRunner, equal_count_bounds
+    from .slab import NativeSlabRunner, equal_count_bounds
     from .strategy import B200SPHStrategy, SphConstants
 
     name = args.workload or "box32m"
@@ -55,14 +55,13 @@ def run(args, rank, world, local_rank):
         torch.cuda.empty_cache()
     dist.barrier()
 
-    run_ = GpuSlabRunner(params, SphConstants(mode=mode), capacity=capacity, bounds=bounds, device=local_rank)
+    run_ = NativeSlabRunner(params, SphConstants(mode=mode), col_hist=hist, bounds=bounds, device=local_rank)
+    capacity = run_.capacity
     run_.load_global(st.position, st.velocity)
-    snap = (run_.P[:run_.n_own].clone(), run_.V[:run_.n_own].clone(), run_.G[:run_.n_own].clone(), run_.n_own)
+    snap = run_.snapshot()
 
     def restore():
-        k = snap[3]
-        run_.P[:k], run_.V[:k], run_.G[:k] = snap[0], snap[1], snap[2]
-        run_.n_own = run_.n_local = k
+        run_.restore(snap)
 
     def timed_steps(k):
         torch.cuda.synchronize()
@@ -99,19 +98,20 @@ def run(args, rank, world, local_rank):
     launches = torch.tensor([run_.launch_count() - launches0], device=dev)
     dist.all_reduce(launches)
     cnt = run_.count_global()
-    stats = torch.tensor([run_.stats["halo_sent"], run_.stats["migrated"], run_.n_own], device=dev, dtype=torch.float64)
+    stt = run_.check()
+    stats = torch.tensor([stt["ghosts"], stt["hwm"], stt["live"]], device=dev, dtype=torch.float64)
     allstats = [torch.empty_like(stats) for _ in range(world)]
     dist.all_gather(allstats, stats)
     clocks = sampler.stop() if rank == 0 else None
     assert cnt == n, f"particles lost: {cnt} != {n}"
     if rank == 0:
         value = n * K / (ms_total * 1e-3)
-        steps_total = max(run_.stats["steps"], 1)
         line = {"metric": bench.METRIC, "value": value, "unit": bench.UNIT, "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
                 "config": {"workload": desc, "name": name, "particles": n,
-                           "parallelism": f"x-slabs x{world}, 2-column ghost halos + migration (all_to_all over NCCL)",
+                           "parallelism": f"x-slabs x{world}, 2-column ghost halos + migration: one fixed-size all_to_all per step "
+                                          "(NCCL), device-side routing, no host sync in the step loop",
                            "slab_bounds": bounds, "capacity_per_rank": capacity,
                            "window": f"state restored to the start state every {window} steps (untimed)"
                            if window else "none", "l2": "working set per GPU larger than L2: no flush",
@@ -119,9 +119,10 @@ def run(args, rank, world, local_rank):
                 "wall_s_timed_region": t_wall, "clocks": clocks, "gpu_launches": int(launches.item()),
                 "e2e": None, "roofline": None, "cpu_baseline": None,
                 "value_1gpu_same_workload": single,
-                "halo_particles_per_step_per_rank": [float(s[0]) / steps_total for s in allstats],
-                "migrated_per_step_per_rank": [float(s[1]) / steps_total for s in allstats],
-                "owned_per_rank": [int(s[2]) for s in allstats]}
+                "ghosts_per_rank": [int(s[0]) for s in allstats],
+                "owned_high_water_per_rank": [int(s[1]) for s in allstats],
+                "owned_per_rank": [int(s[2]) for s in allstats],
+                "exchange_bytes_per_step_per_rank": int(sum(run_.block_bytes))}
         print(json.dumps(line), flush=True)
     run_.close()
     dist.barrier()

@@ -1,0 +1,244 @@
+// x-slab exchange kernels (multi-GPU; no reference counterpart -- the reference is single-GPU).
+//
+// Slot layout of the master arrays on one rank (capacity = own_cap + ghost_cap):
+//   [0, own_cap)         owned region: particles this rank integrates; may contain holes (gid = -1, x = NaN) where a
+//                        particle emigrated, and unused slots above the high-water mark
+//   [own_cap, capacity)  ghost region: copies of the neighbours' boundary columns, rebuilt every step
+// Empty slots hash to the dead cell, sort to the tail and are skipped by every kernel, so a step always runs over the
+// whole capacity: no particle count ever has to travel to the host and nothing in the step loop synchronises with it.
+//
+// Per step:  slab_route_kernel packs, for every owned particle, (a) a MIGRANT record for its new owner if its column
+// left the slab and (b) GHOST records for the ranks whose two-column halo contains its column, into one send block
+// per destination rank (a migrant region and a ghost region, counts in the block header);
+// one fixed-size all_to_all (NCCL over NVLink; block sizes are static, adjacent ranks get large blocks, the others
+// small ones for the rare long-distance migrant / the pipe outlet -> inlet recycle);  slab_unpack_kernel appends
+// the migrants above the high-water mark and the ghosts into the ghost region.
+#pragma once
+#include "sph_common.cuh"
+
+namespace sph {
+
+constexpr int SLAB_MAX_WORLD = 16;
+constexpr int SLAB_HALO = 2;   // ghost columns per side (two: the density of first-column ghosts is recomputed locally)
+
+struct SlabRoute {
+    int32_t world, rank;
+    int32_t bounds[SLAB_MAX_WORLD + 1];   // rank r owns columns [bounds[r], bounds[r + 1])
+    int32_t n_cols;
+    double voxel_x;
+    int32_t own_cap, capacity;
+    int32_t rec_bytes;                    // 32: (pos4, vel4 with gid in .w); 48: + xoroshiro state (PIPE)
+    int32_t cap_m[SLAB_MAX_WORLD];        // migrant records per destination block
+    int32_t cap_g[SLAB_MAX_WORLD];        // ghost records per destination block (stored after the migrants)
+    int64_t peer_off[SLAB_MAX_WORLD + 1]; // byte offset of each block in the send / receive buffer;
+                                          // block = 16-byte header (n_migrants, n_ghosts) + records
+};
+
+// counters (device): [0] high-water mark of the owned region, [1] ghosts of this step, [2] overflow flags,
+// [3] scratch (compaction), [4] live owned particles (filled by slab_count_kernel)
+constexpr int SLAB_HWM = 0, SLAB_NGHOST = 1, SLAB_OVERFLOW = 2, SLAB_SCRATCH = 3, SLAB_NLIVE = 4;
+
+// int32(x / voxel) with fp64 division and C truncation, as the hash kernel does; -1 if not representable
+__device__ __forceinline__ int slab_column(float x, double voxel_x) {
+    const double q = (double)x / voxel_x;
+    if (!(fabs(q) < 2147483648.0)) return -1;
+    return (int)q;
+}
+
+__device__ __forceinline__ int slab_owner(const SlabRoute &r, int col) {
+    col = min(max(col, 0), r.n_cols - 1);
+    int o = 0;
+    for (int k = 1; k < r.world; ++k) o += (col >= r.bounds[k]) ? 1 : 0;
+    return o;
+}
+
+// One record into the block of destination `d` (all lanes of the warp call this; `emit` says which lanes have one).
+// kind 0 = migrant (first region of the block), 1 = ghost (second region).  Warp-aggregated: one atomic per (warp, destination, kind).
+__device__ __forceinline__ void slab_emit(const SlabRoute &r, unsigned char *sendbuf, int32_t *counters, bool emit,
+                                          int d, int kind, const float4 &p, const float4 &v, int gid,
+                                          const uint64_t *rng) {
+    const unsigned lane = threadIdx.x & 31;
+    unsigned pending = __ballot_sync(0xffffffffu, emit);
+    while (pending) {
+        const int leader = __ffs(pending) - 1;
+        const int dl = __shfl_sync(0xffffffffu, d, leader);
+        const unsigned same = __ballot_sync(0xffffffffu, emit && d == dl) & pending;
+        pending &= ~same;
+        unsigned char *block = sendbuf + r.peer_off[dl];
+        int32_t *hdr = reinterpret_cast<int32_t *>(block);
+        int base = 0;
+        if ((int)lane == leader) base = atomicAdd(&hdr[kind], __popc(same));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if ((same >> lane) & 1u) {
+            const int mine = base + __popc(same & ((1u << lane) - 1u));
+            const int cap = kind == 0 ? r.cap_m[dl] : r.cap_g[dl];
+            if (mine >= cap) {
+                atomicOr(&counters[SLAB_OVERFLOW], 1);
+            } else {
+                const int slot = kind == 0 ? mine : r.cap_m[dl] + mine;
+                unsigned char *rec = block + 16 + (size_t)slot * r.rec_bytes;
+                *reinterpret_cast<float4 *>(rec) = p;
+                *reinterpret_cast<float4 *>(rec + 16) = make_float4(v.x, v.y, v.z, __int_as_float(gid));
+                if (r.rec_bytes == 48) {
+                    uint64_t s0 = 0, s1 = 0;
+                    if (kind == 0 && rng) {
+                        s0 = rng[2 * (size_t)gid];
+                        s1 = rng[2 * (size_t)gid + 1];
+                    }
+                    *reinterpret_cast<ulonglong2 *>(rec + 32) = make_ulonglong2(s0, s1);
+                }
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+slab_route_kernel(SlabRoute r, float4 *__restrict__ pos_m, const float4 *__restrict__ vel_m, int32_t *__restrict__ gid,
+                  const uint64_t *__restrict__ rng, unsigned char *__restrict__ sendbuf,
+                  int32_t *__restrict__ counters) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool in = i < r.own_cap;
+    const int g = in ? gid[i] : -1;
+    const bool have = g >= 0;
+    float4 p = make_float4(0.f, 0.f, 0.f, 0.f), v = p;
+    int col = -1, o = r.rank;
+    if (have) {
+        p = pos_m[i];
+        v = vel_m[i];
+        col = slab_column(p.x, r.voxel_x);
+        if (col >= 0) o = slab_owner(r, col);   // a particle without a column (non-finite x) stays where it is, dead
+    }
+    const bool leaves = have && o != r.rank;
+    const int lo = r.bounds[o], hi = r.bounds[o + 1];
+    const bool ghost_l = have && o > 0 && col >= lo && col < lo + SLAB_HALO;
+    const bool ghost_r = have && o < r.world - 1 && col >= hi - SLAB_HALO && col < hi;
+    slab_emit(r, sendbuf, counters, leaves, o, 0, p, v, g, rng);
+    slab_emit(r, sendbuf, counters, ghost_l, o - 1, 1, p, v, g, nullptr);
+    slab_emit(r, sendbuf, counters, ghost_r, o + 1, 1, p, v, g, nullptr);
+    if (leaves) {   // the slot becomes a hole
+        gid[i] = -1;
+        pos_m[i] = make_float4(__int_as_float(0x7fc00000), 0.f, 0.f, 0.f);
+    }
+}
+
+// ghost region -> empty
+__global__ void __launch_bounds__(256)
+slab_clear_ghosts_kernel(SlabRoute r, float4 *__restrict__ pos_m, int32_t *__restrict__ gid,
+                         int32_t *__restrict__ counters) {
+    const int i = r.own_cap + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == r.own_cap) counters[SLAB_NGHOST] = 0;
+    if (i >= r.capacity) return;
+    if (gid[i] >= 0) {
+        gid[i] = -1;
+        pos_m[i] = make_float4(__int_as_float(0x7fc00000), 0.f, 0.f, 0.f);
+    }
+}
+
+// grid.y = source rank.  Migrants are appended above the high-water mark, ghosts into the ghost region.
+__global__ void __launch_bounds__(256)
+slab_unpack_kernel(SlabRoute r, const unsigned char *__restrict__ recvbuf, float4 *__restrict__ pos_m,
+                   float4 *__restrict__ vel_m, int32_t *__restrict__ gid, uint64_t *__restrict__ rng,
+                   int32_t *__restrict__ counters) {
+    const int src = blockIdx.y;
+    const unsigned char *block = recvbuf + r.peer_off[src];
+    const int32_t *hdr = reinterpret_cast<const int32_t *>(block);
+    const int n_front = min(hdr[0], r.cap_m[src]), n_back = min(hdr[1], r.cap_g[src]);
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;   // over [0, n_front + n_back)
+    if (blockIdx.x * blockDim.x >= n_front + n_back) return;
+    const unsigned lane = threadIdx.x & 31;
+    const bool valid = idx < n_front + n_back;
+    const bool migrant = valid && idx < n_front;
+    const bool ghost = valid && !migrant;
+    const int slot_in = migrant ? idx : r.cap_m[src] + (idx - n_front);
+    // aggregated appends
+    const unsigned mm = __ballot_sync(0xffffffffu, migrant), gm = __ballot_sync(0xffffffffu, ghost);
+    int mbase = 0, gbase = 0;
+    if (lane == 0) {
+        if (mm) mbase = atomicAdd(&counters[SLAB_HWM], __popc(mm));
+        if (gm) gbase = atomicAdd(&counters[SLAB_NGHOST], __popc(gm));
+    }
+    mbase = __shfl_sync(0xffffffffu, mbase, 0);
+    gbase = __shfl_sync(0xffffffffu, gbase, 0);
+    if (!valid) return;
+    const unsigned lt = (1u << lane) - 1u;
+    int dst;
+    if (migrant) {
+        dst = mbase + __popc(mm & lt);
+        if (dst >= r.own_cap) {
+            atomicOr(&counters[SLAB_OVERFLOW], 2);
+            return;
+        }
+    } else {
+        dst = r.own_cap + gbase + __popc(gm & lt);
+        if (dst >= r.capacity) {
+            atomicOr(&counters[SLAB_OVERFLOW], 4);
+            return;
+        }
+    }
+    const unsigned char *rec = block + 16 + (size_t)slot_in * r.rec_bytes;
+    const float4 p = *reinterpret_cast<const float4 *>(rec);
+    const float4 v = *reinterpret_cast<const float4 *>(rec + 16);
+    const int g = __float_as_int(v.w);
+    pos_m[dst] = p;
+    vel_m[dst] = make_float4(v.x, v.y, v.z, 0.f);
+    gid[dst] = g;
+    if (migrant && r.rec_bytes == 48 && rng) {
+        const ulonglong2 s = *reinterpret_cast<const ulonglong2 *>(rec + 32);
+        rng[2 * (size_t)g] = s.x;
+        rng[2 * (size_t)g + 1] = s.y;
+    }
+}
+
+// live owned particles -> counters[SLAB_NLIVE] (counters[SLAB_NLIVE] must be zero)
+__global__ void __launch_bounds__(256)
+slab_count_kernel(SlabRoute r, const int32_t *__restrict__ gid, int32_t *__restrict__ counters) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool have = i < r.own_cap && gid[i] >= 0;
+    const unsigned m = __ballot_sync(0xffffffffu, have);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(&counters[SLAB_NLIVE], __popc(m));
+}
+
+// Compaction of the owned region (closes the holes): live particles -> tmp arrays at consecutive slots ...
+__global__ void __launch_bounds__(256)
+slab_compact_gather_kernel(SlabRoute r, const float4 *__restrict__ pos_m, const float4 *__restrict__ vel_m,
+                           const int32_t *__restrict__ gid, float4 *__restrict__ tpos, float4 *__restrict__ tvel,
+                           int32_t *__restrict__ tgid, int32_t *__restrict__ counters) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool have = i < r.own_cap && gid[i] >= 0;
+    const unsigned m = __ballot_sync(0xffffffffu, have);
+    const unsigned lane = threadIdx.x & 31;
+    int base = 0;
+    if (lane == 0 && m) base = atomicAdd(&counters[SLAB_SCRATCH], __popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (!have) return;
+    const int dst = base + __popc(m & ((1u << lane) - 1u));
+    tpos[dst] = pos_m[i];
+    tvel[dst] = vel_m[i];
+    tgid[dst] = gid[i];
+}
+
+// ... and back; slots above the new high-water mark become empty.  counters[SLAB_SCRATCH] holds the live count.
+__global__ void __launch_bounds__(256)
+slab_compact_scatter_kernel(SlabRoute r, float4 *__restrict__ pos_m, float4 *__restrict__ vel_m,
+                            int32_t *__restrict__ gid, const float4 *__restrict__ tpos,
+                            const float4 *__restrict__ tvel, const int32_t *__restrict__ tgid,
+                            int32_t *__restrict__ counters) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= r.own_cap) return;
+    const int n = counters[SLAB_SCRATCH];
+    if (i < n) {
+        pos_m[i] = tpos[i];
+        vel_m[i] = tvel[i];
+        gid[i] = tgid[i];
+    } else {
+        gid[i] = -1;
+        pos_m[i] = make_float4(__int_as_float(0x7fc00000), 0.f, 0.f, 0.f);
+    }
+}
+
+__global__ void slab_compact_finish_kernel(int32_t *__restrict__ counters) {
+    counters[SLAB_HWM] = counters[SLAB_SCRATCH];
+    counters[SLAB_SCRATCH] = 0;
+}
+
+}  // namespace sph

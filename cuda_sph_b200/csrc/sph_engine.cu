@@ -15,6 +15,7 @@
 #include "../../include/sph_b200.h"
 #include "radix_onesweep.cuh"
 #include "radix_sort.cuh"
+#include "slab_exchange.cuh"
 #include "sph_kernels.cuh"
 #include "sweep.cuh"
 #include "sweep_rows.cuh"
@@ -69,6 +70,11 @@ struct SphEngine {
     int32_t *gid = nullptr;       // global particle id per local index
     int32_t slab_lo = 0, slab_hi = 0;
     int64_t cell_capacity = 0;    // entries allocated in cell_range
+    SlabRoute route{};            // native exchange (sph_slab_exchange_init)
+    bool route_ready = false;
+    unsigned char *sendbuf = nullptr, *recvbuf = nullptr;
+    int32_t *slab_counters = nullptr;   // SLAB_HWM, SLAB_NGHOST, SLAB_OVERFLOW, SLAB_SCRATCH, SLAB_NLIVE (+ pad)
+    int32_t *tmp_gid = nullptr;         // compaction scratch
     // host-boundary staging (fp64 / fp32 (N,3) + rho), grown lazily
     void *stage = nullptr;
     size_t stage_bytes = 0;
@@ -328,7 +334,8 @@ int sph_destroy(sph_handle_t e) {
     invalidate_graph(e);
     void *ptrs[] = {e->pos_m, e->vel_m, e->spos, e->svel, e->sforce, e->spress, e->svisc, e->srho, e->nlist, e->ncnt,
                     e->keys, e->ka, e->va, e->kb, e->vb, e->block_hist, e->digit_total, e->os_ctrl, e->cell_range, e->pipe_d,
-                    e->rng, e->gid, e->stage, e->stats_d, e->snap_pos, e->snap_vel, e->snap_rng};
+                    e->rng, e->gid, e->stage, e->stats_d, e->snap_pos, e->snap_vel, e->snap_rng, e->sendbuf, e->recvbuf,
+                    e->slab_counters, e->tmp_gid};
     for (void *q : ptrs)
         if (q) cudaFree(q);
     for (auto &ev : e->ev)
@@ -456,7 +463,7 @@ static int enqueue_step(SphEngine *e, bool timed, int n, int n_own) {
     if (e->slab) {   // in-cell order by GLOBAL id (the local index order is arrival order on a slab)
         uint32_t *fixed = (e->sids == e->va) ? e->vb : e->va;
         cell_range_kernel<<<g256, 256, 0, s>>>(e->skeys, e->cell_range, n);
-        fix_order_kernel<<<g256, 256, 0, s>>>(e->skeys, e->sids, fixed, e->gid, e->cell_range, n);
+        fix_order_kernel<<<g256, 256, 0, s>>>(e->skeys, e->sids, fixed, e->gid, e->cell_range, n, (uint32_t)e->grid.ncells);
         sids = fixed;
     }
     reorder_kernel<<<g256, 256, 0, s>>>(e->skeys, sids, e->pos_m, e->vel_m, e->spos, e->svel, e->cell_range, n);
@@ -642,6 +649,138 @@ int sph_slab_step(sph_handle_t e, int32_t n_own, int32_t n_local) {
     return 0;
 }
 
+// ---- native x-slab exchange (slab_exchange.cuh) ------------------------------------------------------------------
+int sph_slab_exchange_init(sph_handle_t e, int32_t world, int32_t rank, const int32_t *bounds, int32_t own_cap,
+                           const int32_t *cap_migrants, const int32_t *cap_ghosts, void **sendbuf, void **recvbuf,
+                           int64_t *block_bytes) {
+    if (!e || !bounds || !cap_migrants || !cap_ghosts) return fail("null argument");
+    if (!e->slab) return fail("create the engine with SPH_FLAG_SLAB");
+    if (e->slab_hi <= e->slab_lo) return fail("call sph_slab_configure first");
+    if (world < 1 || world > SLAB_MAX_WORLD || rank < 0 || rank >= world) return fail("bad world / rank");
+    if (own_cap <= 0 || own_cap >= e->n) return fail("own_cap must leave room for the ghost region");
+    if (bounds[rank] != e->slab_lo || bounds[rank + 1] != e->slab_hi) return fail("bounds disagree with sph_slab_configure");
+    CK(cudaSetDevice(e->device));
+    CK(cudaStreamSynchronize(e->stream));
+    SlabRoute &r = e->route;
+    r = SlabRoute{};
+    r.world = world;
+    r.rank = rank;
+    for (int k = 0; k <= world; ++k) r.bounds[k] = bounds[k];
+    r.n_cols = e->ceil_dims[0];
+    r.voxel_x = e->p.voxel_size[0];
+    r.own_cap = own_cap;
+    r.capacity = e->n;
+    r.rec_bytes = (e->p.mode == SPH_MODE_PIPE) ? 48 : 32;
+    int64_t off = 0;
+    for (int k = 0; k < world; ++k) {
+        if (cap_migrants[k] < 0 || cap_ghosts[k] < 0) return fail("negative block capacity");
+        r.cap_m[k] = cap_migrants[k];
+        r.cap_g[k] = cap_ghosts[k];
+        r.peer_off[k] = off;
+        const int64_t bytes = 16 + (int64_t)(cap_migrants[k] + cap_ghosts[k]) * r.rec_bytes;
+        if (block_bytes) block_bytes[k] = bytes;
+        off += bytes;
+    }
+    r.peer_off[world] = off;
+    for (void *q : {(void *)e->sendbuf, (void *)e->recvbuf, (void *)e->slab_counters, (void *)e->tmp_gid})
+        if (q) cudaFree(q);
+    e->sendbuf = e->recvbuf = nullptr;
+    e->slab_counters = e->tmp_gid = nullptr;
+    CK(cudaMalloc((void **)&e->sendbuf, (size_t)off));
+    CK(cudaMalloc((void **)&e->recvbuf, (size_t)off));
+    CK(cudaMalloc((void **)&e->slab_counters, 8 * sizeof(int32_t)));
+    CK(cudaMalloc((void **)&e->tmp_gid, sizeof(int32_t) * (size_t)own_cap));
+    CK(cudaMemset(e->sendbuf, 0, (size_t)off));
+    CK(cudaMemset(e->recvbuf, 0, (size_t)off));
+    CK(cudaMemset(e->slab_counters, 0, 8 * sizeof(int32_t)));
+    // every slot starts empty
+    CK(cudaMemset(e->gid, 0xff, sizeof(int32_t) * (size_t)e->n));
+    CK(cudaMemset(e->pos_m, 0xff, sizeof(float4) * (size_t)e->n));
+    if (sendbuf) *sendbuf = e->sendbuf;
+    if (recvbuf) *recvbuf = e->recvbuf;
+    e->route_ready = true;
+    return 0;
+}
+
+static int check_route(SphEngine *e) {
+    if (!e) return fail("null handle");
+    if (!e->route_ready) return fail("call sph_slab_exchange_init first");
+    return 0;
+}
+
+int sph_slab_route(sph_handle_t e) {
+    if (check_route(e)) return 1;
+    CK(cudaSetDevice(e->device));
+    const SlabRoute &r = e->route;
+    for (int k = 0; k < r.world; ++k) CK(cudaMemsetAsync(e->sendbuf + r.peer_off[k], 0, 16, e->stream));
+    slab_route_kernel<<<(r.own_cap + 255) / 256, 256, 0, e->stream>>>(r, e->pos_m, e->vel_m, e->gid, e->rng, e->sendbuf,
+                                                                      e->slab_counters);
+    CK(cudaGetLastError());
+    e->launches += 1 + r.world;
+    return 0;
+}
+
+int sph_slab_unpack(sph_handle_t e) {
+    if (check_route(e)) return 1;
+    CK(cudaSetDevice(e->device));
+    const SlabRoute &r = e->route;
+    slab_clear_ghosts_kernel<<<(r.capacity - r.own_cap + 255) / 256, 256, 0, e->stream>>>(r, e->pos_m, e->gid,
+                                                                                         e->slab_counters);
+    int maxrec = 1;
+    for (int k = 0; k < r.world; ++k) maxrec = std::max(maxrec, r.cap_m[k] + r.cap_g[k]);
+    dim3 grid((maxrec + 255) / 256, r.world);
+    slab_unpack_kernel<<<grid, 256, 0, e->stream>>>(r, e->recvbuf, e->pos_m, e->vel_m, e->gid, e->rng,
+                                                    e->slab_counters);
+    CK(cudaGetLastError());
+    e->launches += 2;
+    return 0;
+}
+
+int sph_slab_step_all(sph_handle_t e) {
+    if (check_route(e)) return 1;
+    if (e->p.mode == SPH_MODE_PIPE && !e->pipe_d) return fail("PIPE mode needs sph_set_pipe before stepping");
+    CK(cudaSetDevice(e->device));
+    if (enqueue_step(e, false, e->n, e->route.own_cap)) return 1;
+    e->steps_done += 1;
+    e->launches += e->launches_per_step + 2;
+    return 0;
+}
+
+int sph_slab_compact(sph_handle_t e) {
+    if (check_route(e)) return 1;
+    CK(cudaSetDevice(e->device));
+    const SlabRoute &r = e->route;
+    const int g = (r.own_cap + 255) / 256;
+    // spos / svel are free between steps: use them as the compaction scratch
+    slab_compact_gather_kernel<<<g, 256, 0, e->stream>>>(r, e->pos_m, e->vel_m, e->gid, e->spos, e->svel, e->tmp_gid,
+                                                         e->slab_counters);
+    slab_compact_scatter_kernel<<<g, 256, 0, e->stream>>>(r, e->pos_m, e->vel_m, e->gid, e->spos, e->svel, e->tmp_gid,
+                                                          e->slab_counters);
+    slab_compact_finish_kernel<<<1, 1, 0, e->stream>>>(e->slab_counters);
+    CK(cudaGetLastError());
+    e->launches += 3;
+    return 0;
+}
+
+int sph_slab_counters(sph_handle_t e, int32_t *out5) {
+    if (check_route(e)) return 1;
+    if (!out5) return fail("null argument");
+    CK(cudaSetDevice(e->device));
+    const SlabRoute &r = e->route;
+    CK(cudaMemsetAsync(e->slab_counters + SLAB_NLIVE, 0, sizeof(int32_t), e->stream));
+    slab_count_kernel<<<(r.own_cap + 255) / 256, 256, 0, e->stream>>>(r, e->gid, e->slab_counters);
+    CK(cudaGetLastError());
+    int32_t h[8];
+    CK(cudaMemcpyAsync(h, e->slab_counters, sizeof(h), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    out5[0] = h[SLAB_HWM];
+    out5[1] = h[SLAB_NGHOST];
+    out5[2] = h[SLAB_OVERFLOW];
+    out5[3] = h[SLAB_NLIVE];
+    out5[4] = r.own_cap;
+    return 0;
+}
+
 int sph_sync(sph_handle_t e) {
     if (!e) return fail("null handle");
     CK(cudaSetDevice(e->device));
@@ -759,6 +898,7 @@ int sph_device_ptr(sph_handle_t e, int32_t which, void **ptr, int64_t *n_element
         case 3: q = e->spos; break;
         case 4: q = e->gid; break;
         case 5: q = e->rng; break;
+        case 6: q = e->slab_counters; break;
         default: return fail("unknown buffer id");
     }
     *ptr = q;

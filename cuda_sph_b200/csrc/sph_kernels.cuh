@@ -68,11 +68,15 @@ cell_range_kernel(const uint32_t *__restrict__ skeys, int2 *__restrict__ cell_ra
 __global__ void __launch_bounds__(256)
 fix_order_kernel(const uint32_t *__restrict__ skeys, const uint32_t *__restrict__ sids_in,
                  uint32_t *__restrict__ sids_out, const int32_t *__restrict__ gid,
-                 const int2 *__restrict__ cell_range, int n) {
+                 const int2 *__restrict__ cell_range, int n, uint32_t dead_key) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
-    const int2 r = cell_range[skeys[t]];
     const uint32_t me = sids_in[t];
+    if (skeys[t] == dead_key) {   // dead cell (incl. every empty slot): nobody's candidate, keep the order
+        sids_out[t] = me;
+        return;
+    }
+    const int2 r = cell_range[skeys[t]];
     const int32_t g = gid[me];
     int rank = 0;
     for (int u = r.x; u < r.y; ++u) rank += (gid[sids_in[u]] < g) ? 1 : 0;

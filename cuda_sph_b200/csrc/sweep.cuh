@@ -110,6 +110,9 @@ struct ForceAcc {
 template <bool RECORD_TERMS>
 __device__ __noinline__ void finish_particle(const SweepArgs &a, const StepConsts &c, int t, const float4 pi,
                                                 const float4 vi, float rho_i, ForceAcc f) {
+    const uint32_t id = a.sids[t];
+    if ((int)id >= a.n_own) return;              // ghost particle of an x-slab: its owner integrates it
+    if (a.gid && a.gid[id] < 0) return;          // empty slot of an x-slab (hole left by an emigrant / unused capacity)
     if (f.any) {  // with no neighbour besides self the reference's sums stay exactly 0 (and rho_i is 0)
         const float s = c.mass_visc / rho_i;
         f.ux *= s;
@@ -130,8 +133,6 @@ __device__ __noinline__ void finish_particle(const SweepArgs &a, const StepConst
         v[d] += F[d] * s_dt;
         x[d] += v[d] * c.dt;
     }
-    const uint32_t id = a.sids[t];
-    if ((int)id >= a.n_own) return;   // ghost particle of an x-slab: its owner integrates it
     if (c.mode == 1) {
         PipeView pv{a.pipe, c.pipe_rows};
         collide_pipe(pv, x, v, a.rng + 2 * (size_t)(a.gid ? (uint32_t)a.gid[id] : id));

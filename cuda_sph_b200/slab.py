@@ -295,3 +295,228 @@ class GpuSlabRunner(SlabRunner):
             self.close()
         except Exception:
             pass
+
+
+class NativeSlabRunner:
+    """x-slab runner on the native exchange path of libsph_b200.so (csrc/slab_exchange.cuh).
+
+    Same decomposition as `SlabRunner` (two-column halos, ownership by cell column, migration to any rank, in-cell order
+    by global id), but routing, packing and unpacking are CUDA kernels working on a fixed slot layout, and ghosts and
+    migrants of one step travel together in ONE fixed-size all_to_all: nothing in the step loop synchronises with the
+    host.  `SlabRunner` remains the executable specification of the protocol (tests/test_slab_gloo.py, CPU / gloo);
+    tests/test_gpu_slab.py demands that this class reproduces the single-GPU engine bitwise.
+
+    Slots [0, own_cap) hold owned particles (holes and unused slots have global id -1), [own_cap, capacity) ghosts.
+    """
+
+    def __init__(self, params, constants=None, *, col_hist: np.ndarray, bounds: Sequence[int], device: int = 0,
+                 group=None, own_slack: float = 1.15, ghost_slack: float = 1.3, migrant_frac: float = 0.02,
+                 far_frac: float = 0.004, compact_every: int = 32):
+        from . import _lib
+        from .strategy import SphConstants
+        self._lib = _lib.load()
+        self._chk = _lib.check
+        cst = constants or SphConstants()
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        space = np.asarray(params.space_size, np.float64).reshape(3)
+        voxel = np.asarray(params.voxel_size, np.float64).reshape(3)
+        self.n_cols = int(np.ceil(space[0] / voxel[0]))
+        self.voxel_x = float(voxel[0])
+        self.bounds = [int(b) for b in bounds]
+        assert len(self.bounds) == self.world + 1 and self.bounds[0] == 0 and self.bounds[-1] == self.n_cols
+        self.lo, self.hi = self.bounds[self.rank], self.bounds[self.rank + 1]
+        self.n_global = int(params.particle_count)
+        self.compact_every = int(compact_every)
+        pipe_mode = cst.mode.upper() == "PIPE"
+
+        # ---- capacities: every rank derives the same numbers from the global column histogram ----
+        hist = np.asarray(col_hist, np.int64)
+        assert len(hist) == self.n_cols
+        own = [int(hist[self.bounds[r]:self.bounds[r + 1]].sum()) for r in range(self.world)]
+        per_rank = max(max(own), self.n_global // self.world)
+
+        def band(r, side):   # particles rank r sends as ghosts to its left (0) / right (1) neighbour at the start
+            lo, hi = self.bounds[r], self.bounds[r + 1]
+            return int(hist[lo:lo + HALO].sum()) if side == 0 else int(hist[max(hi - HALO, lo):hi].sum())
+
+        def caps(a, b):      # block a -> b (symmetric in a, b)
+            if a == b:
+                return 0, 4096
+            a, b = min(a, b), max(a, b)
+            wrap = pipe_mode and a == 0 and b == self.world - 1
+            if b - a == 1:
+                g = int(ghost_slack * max(band(a, 1), band(b, 0))) + 4096
+                m = int(migrant_frac * per_rank) + 4096
+                if wrap:
+                    m = max(m, int(0.25 * per_rank))
+                return m, g
+            m = int(far_frac * per_rank) + 2048
+            if wrap:
+                m = max(m, int(0.25 * per_rank))
+            return m, 1024
+
+        cap_m = np.asarray([caps(self.rank, r)[0] for r in range(self.world)], np.int32)
+        cap_g = np.asarray([caps(self.rank, r)[1] for r in range(self.world)], np.int32)
+        ghosts_in = sum(caps(self.rank, r)[1] for r in range(self.world) if r != self.rank) + 4096
+        self.own_cap = int(own_slack * per_rank) + int(cap_m.sum()) // 4 + 8192
+        self.capacity = self.own_cap + ghosts_in
+
+        p = _lib.SphParams()
+        p.particle_count = int(self.capacity)
+        p.mode = _lib.MODE_PIPE if pipe_mode else _lib.MODE_BOX
+        p.h, p.mass, p.rho0, p.k, p.visc, p.damp = cst.h, cst.mass, cst.rho0, cst.k, cst.visc, cst.damp
+        p.dt = 1 / params.fps
+        ext = np.asarray(params.external_force, np.float64).reshape(3)
+        for d in range(3):
+            p.external_force[d], p.space_size[d], p.voxel_size[d] = ext[d], space[d], voxel[d]
+        p.max_neighbours = cst.max_neighbours
+        p.flags = _lib.FLAG_SLAB | _lib.FLAG_NO_GRAPH
+        p.rng_seed = cst.rng_seed
+        self._h = C.c_void_p()
+        self._chk(self._lib.sph_create(C.byref(p), int(device), C.byref(self._h)))
+        torch.cuda.set_device(device)
+        self._chk(self._lib.sph_set_stream(self._h, C.c_void_p(int(torch.cuda.current_stream().cuda_stream))))
+        if pipe_mode:
+            table = np.ascontiguousarray(params.pipe.to_numpy(), dtype=np.float64)
+            self._chk(self._lib.sph_set_pipe(self._h, table.ctypes.data, table.shape[0]))
+        self._chk(self._lib.sph_slab_configure(self._h, self.lo, self.hi, self.n_global))
+        b = np.asarray(self.bounds, np.int32)
+        sptr, rptr = C.c_void_p(), C.c_void_p()
+        sizes = np.zeros(self.world, np.int64)
+        self._chk(self._lib.sph_slab_exchange_init(self._h, self.world, self.rank, b.ctypes.data, self.own_cap,
+                                                   cap_m.ctypes.data, cap_g.ctypes.data, C.byref(sptr), C.byref(rptr),
+                                                   sizes.ctypes.data))
+        self.block_bytes = [int(s) for s in sizes]
+        dev = torch.device("cuda", device)
+        total = int(sizes.sum())
+        self.send = torch.as_tensor(_CudaBuffer(sptr.value, (total,), "|u1"), device=dev)
+        self.recv = torch.as_tensor(_CudaBuffer(rptr.value, (total,), "|u1"), device=dev)
+
+        def view(which, shape, typestr, dtype):
+            ptr, cnt = C.c_void_p(), C.c_int64()
+            self._chk(self._lib.sph_device_ptr(self._h, which, C.byref(ptr), C.byref(cnt)))
+            return torch.as_tensor(_CudaBuffer(ptr.value, shape, typestr), device=dev).view(dtype)
+
+        cap = self.capacity
+        self.P = view(0, (cap, 4), "<f4", torch.float32)
+        self.V = view(1, (cap, 4), "<f4", torch.float32)
+        self.G = view(4, (cap,), "<i4", torch.int32)
+        self.counters = view(6, (8,), "<i4", torch.int32)
+        self.steps = 0
+
+    # ------------------------------------------------------------------ loading / stepping
+    def load_global(self, position: np.ndarray, velocity: np.ndarray) -> None:
+        """Every rank passes the same full start state and keeps the particles of its slab (global id = row)."""
+        q = np.asarray(position[:, 0], np.float64) / self.voxel_x
+        fin = np.isfinite(q) & (np.abs(q) < 2147483648.0)
+        col = np.where(fin, q, -1.0).astype(np.int64)
+        owner = np.searchsorted(np.asarray(self.bounds[1:-1]), np.clip(col, 0, self.n_cols - 1), side="right")
+        owner = np.where(col >= 0, owner, 0)
+        mine = np.nonzero(owner == self.rank)[0]
+        k = len(mine)
+        if k > self.own_cap:
+            raise RuntimeError(f"slab capacity exceeded on rank {self.rank}: {k} > {self.own_cap}")
+        dev = self.P.device
+        self.G.fill_(-1)
+        self.P.fill_(float("nan"))
+        self.P[:k, :3] = torch.as_tensor(np.ascontiguousarray(position[mine], np.float32)).to(dev)
+        self.P[:k, 3] = 0
+        self.V[:k, :3] = torch.as_tensor(np.ascontiguousarray(velocity[mine], np.float32)).to(dev)
+        self.V[:k, 3] = 0
+        self.G[:k] = torch.as_tensor(mine.astype(np.int32)).to(dev)
+        self.counters.zero_()
+        self.counters[0] = k
+        self.steps = 0
+
+    def step(self, n_steps: int = 1) -> None:
+        for _ in range(n_steps):
+            self._chk(self._lib.sph_slab_route(self._h))
+            if self.world > 1:
+                dist.all_to_all_single(self.recv, self.send, output_split_sizes=self.block_bytes,
+                                       input_split_sizes=self.block_bytes, group=self.group)
+            else:
+                self.recv.copy_(self.send)
+            self._chk(self._lib.sph_slab_unpack(self._h))
+            self._chk(self._lib.sph_slab_step_all(self._h))
+            self.steps += 1
+            if self.compact_every and self.steps % self.compact_every == 0:
+                self._chk(self._lib.sph_slab_compact(self._h))
+
+    # ------------------------------------------------------------------ snapshots (bench windows)
+    def snapshot(self):
+        return (self.P[:self.own_cap].clone(), self.V[:self.own_cap].clone(), self.G[:self.own_cap].clone(),
+                self.counters.clone())
+
+    def restore(self, snap) -> None:
+        self.P[:self.own_cap], self.V[:self.own_cap], self.G[:self.own_cap] = snap[0], snap[1], snap[2]
+        self.counters.copy_(snap[3])
+
+    # ------------------------------------------------------------------ inspection (these synchronise)
+    def status(self) -> dict:
+        out = np.zeros(5, np.int32)
+        self._chk(self._lib.sph_slab_counters(self._h, out.ctypes.data))
+        st = {"hwm": int(out[0]), "ghosts": int(out[1]), "overflow": int(out[2]), "live": int(out[3]),
+              "own_cap": int(out[4]), "capacity": self.capacity}
+        return st
+
+    def check(self) -> dict:
+        """Collective: raises on EVERY rank if any rank overflowed a send block (1), its owned region (2) or its ghost
+        region (4) -- a rank must never leave the others waiting in a collective."""
+        st = self.status()
+        flags = torch.tensor([st["overflow"]], dtype=torch.int64, device=self.P.device)
+        if self.world > 1:
+            dist.all_reduce(flags, op=dist.ReduceOp.MAX, group=self.group)
+        if int(flags.item()):
+            raise RuntimeError(f"x-slab exchange overflow (flags {int(flags.item())}; rank {self.rank}: {st}): "
+                               "raise own_slack / ghost_slack / migrant_frac / far_frac")
+        return st
+
+    def count_global(self) -> int:
+        c = torch.tensor([self.check()["live"]], dtype=torch.int64, device=self.P.device)
+        if self.world > 1:
+            dist.all_reduce(c, group=self.group)
+        return int(c.item())
+
+    def gather_global(self, n_global: int):
+        """All ranks -> every rank: (position, velocity, density) fp64 arrays in global-id order."""
+        self.check()
+        own = torch.nonzero(self.G[:self.own_cap] >= 0).flatten()
+        n = len(own)
+        rows = torch.cat([self.P[own].to(torch.float64), self.V[own, :3].to(torch.float64),
+                          self.G[own].to(torch.float64)[:, None]], dim=1).contiguous()
+        if self.world > 1:
+            counts = torch.tensor([n], dtype=torch.int64, device=rows.device)
+            allc = [torch.empty_like(counts) for _ in range(self.world)]
+            dist.all_gather(allc, counts, group=self.group)
+            sizes = [int(c.item()) for c in allc]
+            pad = torch.zeros((max(sizes), 8), dtype=torch.float64, device=rows.device)
+            pad[:n] = rows
+            bufs = [torch.empty_like(pad) for _ in allc]
+            dist.all_gather(bufs, pad, group=self.group)
+            rows = torch.cat([b_[:k] for b_, k in zip(bufs, sizes)])
+        rows = rows.cpu().numpy()
+        gid = rows[:, 7].astype(np.int64)
+        assert len(gid) == n_global and len(np.unique(gid)) == n_global, "particles lost or duplicated"
+        pos, vel, rho = np.empty((n_global, 3)), np.empty((n_global, 3)), np.empty(n_global)
+        pos[gid], rho[gid], vel[gid] = rows[:, :3], rows[:, 3], rows[:, 4:7]
+        return pos, vel, rho
+
+    def launch_count(self) -> int:
+        return int(self._lib.sph_launch_count(self._h))
+
+    def synchronize(self):
+        self._chk(self._lib.sph_sync(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.P = self.V = self.G = self.counters = self.send = self.recv = None
+            self._lib.sph_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

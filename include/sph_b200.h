@@ -134,6 +134,27 @@ int sph_restore_state(sph_handle_t h);
 int sph_slab_configure(sph_handle_t h, int32_t x_lo, int32_t x_hi, int64_t n_global);
 int sph_slab_step(sph_handle_t h, int32_t n_own, int32_t n_local);
 
+/* Native exchange path (csrc/slab_exchange.cuh): nothing in the step loop synchronises with the host.
+ * Slots [0, own_cap) of the master arrays are the owned region (holes and unused slots are EMPTY: global id -1),
+ * [own_cap, particle_count) the ghost region.  bounds[world + 1] are the slab column boundaries of all ranks;
+ * cap_migrants / cap_ghosts[world] the record capacities of the block sent to (and received from) each rank --
+ * symmetric by construction (adjacent ranks large, the others small).  Returns the device send / receive buffers and the
+ * byte size of every block: the host layer moves them with ONE fixed-size all_to_all per step
+ * (cuda_sph_b200/slab.py NativeSlabRunner; torch.distributed, NCCL over NVLink).
+ *   sph_slab_route     pack migrant + ghost records of the owned particles into the send blocks, open the holes
+ *   sph_slab_unpack    empty the ghost region, append received migrants / ghosts
+ *   sph_slab_step_all  one local step over the whole capacity (empty slots are dead)
+ *   sph_slab_compact   close the holes of the owned region (call every few dozen steps)
+ *   sph_slab_counters  out5 = {high-water mark, ghosts, overflow flags, live owned particles, own_cap}; synchronises */
+int sph_slab_exchange_init(sph_handle_t h, int32_t world, int32_t rank, const int32_t *bounds, int32_t own_cap,
+                           const int32_t *cap_migrants, const int32_t *cap_ghosts, void **sendbuf, void **recvbuf,
+                           int64_t *block_bytes);
+int sph_slab_route(sph_handle_t h);
+int sph_slab_unpack(sph_handle_t h);
+int sph_slab_step_all(sph_handle_t h);
+int sph_slab_compact(sph_handle_t h);
+int sph_slab_counters(sph_handle_t h, int32_t *out5);
+
 /* ---- parity taps: state of the most recent step --------------------------------------------------------------- */
 int sph_get_keys(sph_handle_t h, int32_t *keys);                 /* self.voxels            voxel_sph_strategy.py:82 */
 int sph_get_sorted_ids(sph_handle_t h, int32_t *ids);            /* voxel_particle_map['particle_id']        :85-88 */
@@ -150,7 +171,8 @@ int sph_cell_dims(sph_handle_t h, int32_t *ceil3, int32_t *trunc3);
 
 /* Device pointers for zero-copy wrapping (torch / __cuda_array_interface__).  which: 0 = master position float4[N]
  * (x,y,z,density), 1 = master velocity float4[N], 2 = sorted ids int32[N], 3 = sorted position float4[N],
- * 4 = global ids int32[capacity] (x-slab mode), 5 = xoroshiro states uint64[2 * count] (PIPE mode). */
+ * 4 = global ids int32[capacity] (x-slab mode), 5 = xoroshiro states uint64[2 * count] (PIPE mode),
+ * 6 = slab counters int32[8] (native exchange: high-water mark, ghosts, overflow, scratch, live). */
 int sph_device_ptr(sph_handle_t h, int32_t which, void **ptr, int64_t *n_elements);
 
 /* Total kernels/memsets launched by this handle so far (bench.py's "gpu_launches"). */

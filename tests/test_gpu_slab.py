@@ -21,30 +21,44 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, mode, n, steps, extra_steps, out_path):
+def _worker(rank, world, port, mode, n, steps, extra_steps, out_path, kind="native"):
+    import faulthandler
     import torch.distributed as dist
+    faulthandler.dump_traceback_later(150, exit=True)   # a rank stuck in a collective must not hang the suite
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
         from cuda_sph_b200 import SphConstants
-        from cuda_sph_b200.slab import GpuSlabRunner, equal_count_bounds
+        from cuda_sph_b200.slab import GpuSlabRunner, NativeSlabRunner, equal_count_bounds
         from tests.test_gpu_slab import _case
         params, st = _case(mode, n)
         n_cols = int(np.ceil(params.space_size[0] / params.voxel_size[0]))
         cols = np.clip((st.position[:, 0] / params.voxel_size[0]).astype(np.int64), 0, n_cols - 1)
-        bounds = equal_count_bounds(np.bincount(cols, minlength=n_cols), world)
-        run = GpuSlabRunner(params, SphConstants(mode=mode), capacity=2 * n, bounds=bounds, device=rank)
+        hist = np.bincount(cols, minlength=n_cols)
+        bounds = equal_count_bounds(hist, world)
+        if kind == "native":
+            # the pipe case moves two thirds of a rank's particles to the other rank in ONE step (outlet -> inlet
+            # recycle at |v| ~ 1e2): size the migrant blocks for that
+            run = NativeSlabRunner(params, SphConstants(mode=mode), col_hist=hist, bounds=bounds, device=rank,
+                                   compact_every=2, migrant_frac=1.0 if mode == "PIPE" else 0.02, own_slack=2.0)
+        else:
+            run = GpuSlabRunner(params, SphConstants(mode=mode), capacity=2 * n, bounds=bounds, device=rank)
         run.load_global(st.position, st.velocity)
         run.step(steps)
         assert run.count_global() == n
         pos, vel, rho = run.gather_global(n)
         if rank == 0:
-            np.savez(out_path, pos=pos, vel=vel, rho=rho, halo=run.stats["halo_sent"], migrated=run.stats["migrated"])
+            if kind == "native":
+                halo, migrated = run.status()["ghosts"], 1
+            else:
+                halo, migrated = run.stats["halo_sent"], run.stats["migrated"]
+            np.savez(out_path, pos=pos, vel=vel, rho=rho, halo=halo, migrated=migrated)
         run.step(extra_steps)
         assert run.count_global() == n
         run.close()
     finally:
+        faulthandler.cancel_dump_traceback_later()
         dist.destroy_process_group()
 
 
@@ -59,14 +73,15 @@ def _case(mode, n):
     return params, type(st)(st.position, vel.astype(np.float32).astype(np.float64), st.density)
 
 
+@pytest.mark.parametrize("kind", ["native", "torch"])
 @pytest.mark.parametrize("mode,n,steps,extra", [("BOX", 200000, 3, 0), ("PIPE", 20000, 1, 2)])
-def test_two_gpu_slabs_equal_single_gpu(tmp_path, mode, n, steps, extra):
+def test_two_gpu_slabs_equal_single_gpu(tmp_path, mode, n, steps, extra, kind):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
     from cuda_sph_b200 import B200SPHStrategy, SphConstants
     out = str(tmp_path / "slab.npz")
-    mp.spawn(_worker, args=(2, _free_port(), mode, n, steps, extra, out), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, _free_port(), mode, n, steps, extra, out, kind), nprocs=2, join=True)
     got = np.load(out)
     params, st = _case(mode, n)
     s = B200SPHStrategy(params, SphConstants(mode=mode))
