@@ -59,6 +59,7 @@ EXPORTS = {
     "sph_slab_route": (C.c_int, [_H]),
     "sph_slab_unpack": (C.c_int, [_H]),
     "sph_slab_step_all": (C.c_int, [_H]),
+    "sph_slab_step_all_timed": (C.c_int, [_H, C.POINTER(SphTimings)]),
     "sph_slab_compact": (C.c_int, [_H]),
     "sph_slab_counters": (C.c_int, [_H, _P]),
     "sph_get_keys": (C.c_int, [_H, _P]),

@@ -98,6 +98,16 @@ def run(args, rank, world, local_rank):
     launches = torch.tensor([run_.launch_count() - launches0], device=dev)
     dist.all_reduce(launches)
     cnt = run_.count_global()
+    # per-phase breakdown (one extra window, CUDA events around every phase, max over ranks)
+    restore()
+    acc = {}
+    for _ in range(window or 4):
+        for k_, v_ in run_.step_timed().items():
+            acc[k_] = acc.get(k_, 0.0) + v_ / (window or 4)
+    keys_ = sorted(acc)
+    bt = torch.tensor([acc[k_] for k_ in keys_], device=dev, dtype=torch.float64)
+    dist.all_reduce(bt, op=dist.ReduceOp.MAX)
+    breakdown = {k_: float(v_) for k_, v_ in zip(keys_, bt.tolist())}
     stt = run_.check()
     stats = torch.tensor([stt["ghosts"], stt["hwm"], stt["live"]], device=dev, dtype=torch.float64)
     allstats = [torch.empty_like(stats) for _ in range(world)]
@@ -122,7 +132,8 @@ def run(args, rank, world, local_rank):
                 "ghosts_per_rank": [int(s[0]) for s in allstats],
                 "owned_high_water_per_rank": [int(s[1]) for s in allstats],
                 "owned_per_rank": [int(s[2]) for s in allstats],
-                "exchange_bytes_per_step_per_rank": int(sum(run_.block_bytes))}
+                "exchange_bytes_per_step_per_rank": int(sum(run_.block_bytes)),
+                "phase_ms_max_over_ranks": breakdown}
         print(json.dumps(line), flush=True)
     run_.close()
     dist.barrier()

@@ -746,6 +746,30 @@ int sph_slab_step_all(sph_handle_t e) {
     return 0;
 }
 
+int sph_slab_step_all_timed(sph_handle_t e, SphTimings *t) {
+    if (check_route(e)) return 1;
+    if (!t) return fail("timings is NULL");
+    if (e->p.mode == SPH_MODE_PIPE && !e->pipe_d) return fail("PIPE mode needs sph_set_pipe before stepping");
+    CK(cudaSetDevice(e->device));
+    memset(t, 0, sizeof(*t));
+    if (enqueue_step(e, true, e->n, e->route.own_cap)) return 1;
+    CK(cudaEventSynchronize(e->ev[5]));
+    float ms[5];
+    for (int k = 0; k < 5; ++k) CK(cudaEventElapsedTime(&ms[k], e->ev[k], e->ev[k + 1]));
+    t->hash_ms = ms[0];
+    t->sort_ms = ms[1];
+    t->reorder_ms = ms[2];
+    t->density_ms = ms[3];
+    t->force_ms = ms[4];
+    CK(cudaEventElapsedTime(&t->total_ms, e->ev[0], e->ev[5]));
+    t->steps = 1;
+    t->launches_per_step = e->launches_per_step + 2;
+    t->sort_passes = e->passes;
+    e->steps_done += 1;
+    e->launches += e->launches_per_step + 2;
+    return 0;
+}
+
 int sph_slab_compact(sph_handle_t e) {
     if (check_route(e)) return 1;
     CK(cudaSetDevice(e->device));

@@ -310,8 +310,8 @@ class NativeSlabRunner:
     """
 
     def __init__(self, params, constants=None, *, col_hist: np.ndarray, bounds: Sequence[int], device: int = 0,
-                 group=None, own_slack: float = 1.15, ghost_slack: float = 1.3, migrant_frac: float = 0.02,
-                 far_frac: float = 0.004, compact_every: int = 32):
+                 group=None, own_slack: float = 1.08, ghost_slack: float = 1.4, migrant_frac: float = 0.02,
+                 far_frac: float = 0.005, compact_every: int = 16):
         from . import _lib
         from .strategy import SphConstants
         self._lib = _lib.load()
@@ -342,8 +342,8 @@ class NativeSlabRunner:
             return int(hist[lo:lo + HALO].sum()) if side == 0 else int(hist[max(hi - HALO, lo):hi].sum())
 
         def caps(a, b):      # block a -> b (symmetric in a, b)
-            if a == b:
-                return 0, 4096
+            if a == b:   # ghosts for myself: my emigrants that stop inside the neighbour's boundary band (most do)
+                return 0, 2 * (int(migrant_frac * per_rank) + 4096)
             a, b = min(a, b), max(a, b)
             wrap = pipe_mode and a == 0 and b == self.world - 1
             if b - a == 1:
@@ -359,8 +359,10 @@ class NativeSlabRunner:
 
         cap_m = np.asarray([caps(self.rank, r)[0] for r in range(self.world)], np.int32)
         cap_g = np.asarray([caps(self.rank, r)[1] for r in range(self.world)], np.int32)
-        ghosts_in = sum(caps(self.rank, r)[1] for r in range(self.world) if r != self.rank) + 4096
-        self.own_cap = int(own_slack * per_rank) + int(cap_m.sum()) // 4 + 8192
+        # the ghost REGION is sized for the expected halo (the blocks carry more slack: they are only wire volume)
+        expected = sum(max(band(self.rank + d, 1 if d < 0 else 0), 0) for d in (-1, 1) if 0 <= self.rank + d < self.world)
+        ghosts_in = int(1.4 * expected) + 2 * (int(migrant_frac * per_rank) + 4096) + 8192
+        self.own_cap = int(own_slack * per_rank) + 8192
         self.capacity = self.own_cap + ghosts_in
 
         p = _lib.SphParams()
@@ -443,6 +445,30 @@ class NativeSlabRunner:
             self.steps += 1
             if self.compact_every and self.steps % self.compact_every == 0:
                 self._chk(self._lib.sph_slab_compact(self._h))
+
+    def step_timed(self) -> dict:
+        """One step with CUDA events around every phase (synchronises; for the breakdown in bench.py, not for `value`)."""
+        from . import _lib
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        ev[0].record()
+        self._chk(self._lib.sph_slab_route(self._h))
+        ev[1].record()
+        if self.world > 1:
+            dist.all_to_all_single(self.recv, self.send, output_split_sizes=self.block_bytes,
+                                   input_split_sizes=self.block_bytes, group=self.group)
+        else:
+            self.recv.copy_(self.send)
+        ev[2].record()
+        self._chk(self._lib.sph_slab_unpack(self._h))
+        ev[3].record()
+        t = _lib.SphTimings()
+        self._chk(self._lib.sph_slab_step_all_timed(self._h, C.byref(t)))
+        torch.cuda.synchronize()
+        self.steps += 1
+        out = {"route_ms": ev[0].elapsed_time(ev[1]), "all_to_all_ms": ev[1].elapsed_time(ev[2]),
+               "unpack_ms": ev[2].elapsed_time(ev[3])}
+        out.update({k: getattr(t, k) for k in ("hash_ms", "sort_ms", "reorder_ms", "density_ms", "force_ms")})
+        return out
 
     # ------------------------------------------------------------------ snapshots (bench windows)
     def snapshot(self):

@@ -152,6 +152,7 @@ int sph_slab_exchange_init(sph_handle_t h, int32_t world, int32_t rank, const in
 int sph_slab_route(sph_handle_t h);
 int sph_slab_unpack(sph_handle_t h);
 int sph_slab_step_all(sph_handle_t h);
+int sph_slab_step_all_timed(sph_handle_t h, SphTimings *t); /* same, with per-stage CUDA events; synchronises */
 int sph_slab_compact(sph_handle_t h);
 int sph_slab_counters(sph_handle_t h, int32_t *out5);
 

@@ -41,7 +41,7 @@ def _worker(rank, world, port, mode, n, steps, extra_steps, out_path, kind="nati
             # the pipe case moves two thirds of a rank's particles to the other rank in ONE step (outlet -> inlet
             # recycle at |v| ~ 1e2): size the migrant blocks for that
             run = NativeSlabRunner(params, SphConstants(mode=mode), col_hist=hist, bounds=bounds, device=rank,
-                                   compact_every=2, migrant_frac=1.0 if mode == "PIPE" else 0.02, own_slack=2.0)
+                                   compact_every=2, migrant_frac=1.0 if mode == "PIPE" else 0.05, own_slack=2.0)
         else:
             run = GpuSlabRunner(params, SphConstants(mode=mode), capacity=2 * n, bounds=bounds, device=rank)
         run.load_global(st.position, st.velocity)
