@@ -108,6 +108,40 @@ def run(args, rank, world, local_rank):
     bt = torch.tensor([acc[k_] for k_ in keys_], device=dev, dtype=torch.float64)
     dist.all_reduce(bt, op=dist.ReduceOp.MAX)
     breakdown = {k_: float(v_) for k_, v_ in zip(keys_, bt.tolist())}
+    # ---- e2e: every step starts from HOST buffers (fp64, pinned) and ends in them: H2D of the rank's owned particles,
+    #      exchange + step, D2H of the owned region; wall clock, max over ranks ----
+    k0 = int(snap[3][0].item())
+    hp = snap[0][:k0, :3].double().cpu().pin_memory()
+    hv = snap[1][:k0, :3].double().cpu().pin_memory()
+    own_cap = run_.own_cap
+    op_ = torch.empty((own_cap, 4), dtype=torch.float64).pin_memory()
+    ov_ = torch.empty((own_cap, 3), dtype=torch.float64).pin_memory()
+    og_ = torch.empty((own_cap,), dtype=torch.int32).pin_memory()
+    KE = min(K, 8)
+    e2e_s, d2h_bytes = 0.0, 0
+    for i in range(-2, KE):
+        restore()                                   # slot layout of the start state (ids, counters); untimed
+        torch.cuda.synchronize()
+        dist.barrier()
+        t0 = time.perf_counter()
+        run_.P[:k0, :3] = hp.to(dev, non_blocking=True).float()
+        run_.V[:k0, :3] = hv.to(dev, non_blocking=True).float()
+        run_.step(1)
+        hw = int(run_.counters[0].item())           # owned slots in use after the step (device -> host read)
+        op_[:hw].copy_(run_.P[:hw].double(), non_blocking=True)
+        ov_[:hw].copy_(run_.V[:hw, :3].double(), non_blocking=True)
+        og_[:hw].copy_(run_.G[:hw], non_blocking=True)
+        torch.cuda.synchronize()
+        if i >= 0:
+            e2e_s += time.perf_counter() - t0
+            d2h_bytes = hw * (32 + 24 + 4)
+    et = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+    dist.all_reduce(et, op=dist.ReduceOp.MAX)
+    e2e = {"value": n * KE / float(et.item()), "unit": bench.UNIT, "h2d_bytes_per_step": 48 * k0,
+           "d2h_bytes_per_step": d2h_bytes, "steps": KE, "ms_per_step": float(et.item()) / KE * 1e3,
+           "api": "per rank: pinned fp64 (N_own,3) position/velocity -> device, NativeSlabRunner.step(1), owned region -> "
+                  "pinned fp64 host (bytes are rank 0's)"}
+    restore()
     stt = run_.check()
     stats = torch.tensor([stt["ghosts"], stt["hwm"], stt["live"]], device=dev, dtype=torch.float64)
     allstats = [torch.empty_like(stats) for _ in range(world)]
@@ -115,6 +149,15 @@ def run(args, rank, world, local_rank):
     clocks = sampler.stop() if rank == 0 else None
     assert cnt == n, f"particles lost: {cnt} != {n}"
     if rank == 0:
+        hbm_peak, peak_src = bench.peaks()
+        own_max = max(int(s_[2]) for s_ in allstats)
+        dom = "density" if breakdown["density_ms"] >= breakdown["force_ms"] else "force"
+        gbs = bench.BYTES[dom] * own_max / (breakdown[dom + "_ms"] * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": dom + "_rows_kernel", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
+                    "algorithmic_bytes_per_particle": bench.BYTES[dom], "kernel_ms": breakdown[dom + "_ms"],
+                    "note": "slowest rank: owned particles of that rank x algorithmic bytes / its kernel time; the "
+                            "sweeps are FP32-issue / latency bound, not HBM bound (DESIGN.md section 4)"}
         value = n * K / (ms_total * 1e-3)
         line = {"metric": bench.METRIC, "value": value, "unit": bench.UNIT, "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -127,7 +170,7 @@ def run(args, rank, world, local_rank):
                            if window else "none", "l2": "working set per GPU larger than L2: no flush",
                            "timing": "CUDA events per window, max over ranks, barrier + synchronize on both sides"},
                 "wall_s_timed_region": t_wall, "clocks": clocks, "gpu_launches": int(launches.item()),
-                "e2e": None, "roofline": None, "cpu_baseline": None,
+                "e2e": e2e, "roofline": roofline, "cpu_baseline": None,
                 "value_1gpu_same_workload": single,
                 "ghosts_per_rank": [int(s[0]) for s in allstats],
                 "owned_high_water_per_rank": [int(s[1]) for s in allstats],
