@@ -29,6 +29,7 @@ struct StepConsts {
     float h;
     float h2_lo, h2_hi;  // band around h^2 inside which the fp64 predicate decides
     float h2;
+    float h2_near;       // above this r^2 the poly6 term (h^2 - r^2)^3 is evaluated from an fp64 r^2 (cancellation)
     float w_mass;        // W_CONST * MASS                       (config.py:27, voxel_kernels.py:132)
     float grad_c;        // GRAD_W_CONST                         (config.py:28)
     float lap_c;         // LAP_W_CONST                          (config.py:29)
@@ -36,6 +37,7 @@ struct StepConsts {
     float mass_visc;     // MASS * VISC                          (voxel_kernels.py:208)
     // fp64 epilogue constants
     double r2_max;       // largest double r2 with sqrt(r2) <= INF_R (voxel_kernels.py:20-26)
+    double h2_d;         // INF_R^2 in fp64
     double dt;
     double ext[3];
     double space[3];

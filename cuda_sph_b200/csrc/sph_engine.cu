@@ -221,6 +221,8 @@ int sph_create(const SphParams *params, int device, sph_handle_t *out) {
     StepConsts &c = e->consts;
     c.h = (float)h;
     c.h2 = (float)(h * h);
+    c.h2_near = (float)(h * h * 0.98);
+    c.h2_d = h * h;
     c.h2_lo = (float)(h * h * (1.0 - 1e-5));
     c.h2_hi = (float)(h * h * (1.0 + 1e-5));
     c.w_mass = (float)(315.0 / (64.0 * M_PI * std::pow(h, 9.0)) * params->mass);

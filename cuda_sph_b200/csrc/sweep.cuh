@@ -61,6 +61,24 @@ __device__ __noinline__ bool in_range_exact(float ax, float ay, float az, float 
     return r2 <= r2_max;
 }
 
+// fp64 r^2 of two fp32 points, same operation order as in_range_exact
+__device__ __noinline__ double r2_exact(float ax, float ay, float az, float bx, float by, float bz) {
+    const double dx = (double)ax - (double)bx, dy = (double)ay - (double)by, dz = (double)az - (double)bz;
+    return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+}
+
+// poly6 term (h^2 - r^2)^3.  Close to the cut-off h^2 - r^2 cancels: there it is formed from the fp64 r^2 (the reference
+// is fp64 throughout), which keeps the density of a particle whose only neighbours sit at the cut-off within tolerance.
+__device__ __forceinline__ float poly6_term(const StepConsts &c, float r2, float ax, float ay, float az, float bx,
+                                            float by, float bz) {
+    if (r2 > c.h2_near) {
+        const double d = c.h2_d - r2_exact(ax, ay, az, bx, by, bz);
+        return (float)(d * d * d);
+    }
+    const float d = c.h2 - r2;
+    return d * d * d;
+}
+
 __device__ __forceinline__ float pressure_coeff(const StepConsts &c, float rho) {
     return c.k * (rho - c.rho0) / (rho * rho);   // p / rho^2 with p = K (rho - RHO_0)
 }
@@ -180,8 +198,7 @@ __device__ __noinline__ int thread_walk(const SweepArgs &a, const GridDesc &g, c
                                 const float4 vj = __ldg(&a.svel[j]);
                                 f.pair(c, ddx, ddy, ddz, r2, a_i, pressure_coeff(c, rho_j), c.lap_c / rho_j, vi, vj);
                             } else {
-                                const float d = c.h2 - r2;
-                                dens = fmaf(d * d, d, dens);
+                                dens += poly6_term(c, r2, pi.x, pi.y, pi.z, pj.x, pj.y, pj.z);
                             }
                         }
                         if (++cnt >= kMaxNeighbours) return cnt;

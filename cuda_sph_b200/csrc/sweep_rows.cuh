@@ -354,10 +354,7 @@ density_rows_kernel(const SweepArgs a, const GridDesc g, const StepConsts c) {
                     const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
                     if (r2 > c.h2_lo && !in_range_exact(pj.x, pj.y, pj.z, cj.x, cj.y, cj.z, c.r2_max)) continue;
                     lrow[k++] = (uint16_t)slot;
-                    if (slot != selfj) {
-                        const float d = c.h2 - r2;
-                        dens = fmaf(d * d, d, dens);
-                    }
+                    if (slot != selfj) dens += poly6_term(c, r2, pj.x, pj.y, pj.z, cj.x, cj.y, cj.z);
                 }
                 uint8_t cflag = (uint8_t)k;
                 if (k < kMaxNeighbours && kept >= RB_KEEP) {

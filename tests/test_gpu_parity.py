@@ -5,6 +5,8 @@ neighbour counts; density relative error <= 1e-4; force / velocity / position pe
 for one step (fp32 engine vs the fp64 reference), NaN == NaN.  Typical measured errors are 1e-7..1e-6; the worst case
 for density (1.3e-5) is a particle whose only neighbour sits just inside the cut-off, where (h^2 - r^2)^3 cancels.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -210,4 +212,113 @@ def test_full_size_properties_1m():
     out = s.download()
     assert np.isfinite(out.position).all() and np.isfinite(out.density).all()
     assert (out.position >= 0).all() and (out.position <= np.asarray(params.space_size)).all()
+    s.close()
+
+
+@pytest.mark.parametrize("n,ppc,seed", [(40000, 60.0, 31), (40000, 140.0, 32)])
+def test_dense_cells_take_the_fallback_passes(n, ppc, seed):
+    """Cells too dense for a whole-CTA row plan (60/cell: four 32-particle passes) or for any plan (140/cell: the
+    one-thread walk) must give the same answer as everything else."""
+    from cuda_sph_b200 import workloads
+    from oracle import oracle as orc
+    params, st = workloads.uniform_box(n, ppc, seed)
+    s = _strategy(n, "BOX", params.space_size, params.voxel_size, params.external_force, params.fps)
+    s.compute_next_state(st)
+    P = orc.OracleParams(n=n, space=tuple(params.space_size), dt=1 / params.fps)
+    # grid / sort / neighbour counts stay bit-exact; at 140 particles per cell (rho ~ 18 rho_0, |F| ~ 1e4) the fp32
+    # pair sums cancel harder and the box is only 14 units wide, so the RELATIVE position tolerance is widened there
+    _check_against(s, _oracle_ref(P, st.position, st.velocity), vec=1e-4 if ppc < 100 else 5e-4)
+    s.close()
+
+
+def test_unaligned_grid_quirk_q2():
+    """space_size not a multiple of voxel_size: keys use the ceil dims, the neighbour walk the trunc dims (reference
+    quirk Q2, voxel_sph_strategy.py:70-73 vs :110-116) -- reproduced literally, via the walk path."""
+    from cuda_sph_b200.data_classes import SimulationState
+    from oracle import oracle as orc
+    n = 6000
+    rng = np.random.default_rng(33)
+    space = [21.0, 19.0, 23.0]
+    pos = (rng.random((n, 3), dtype=np.float32) * np.asarray(space, np.float32)).astype(np.float64)
+    vel = rng.uniform(-3, 3, (n, 3)).astype(np.float32).astype(np.float64)
+    s = _strategy(n, "BOX", space, [2, 2, 2], [0, -2, 0], 20)
+    s.compute_next_state(SimulationState(pos, vel, np.zeros(n)))
+    P = orc.OracleParams(n=n, space=tuple(space), dt=1 / 20)
+    _check_against(s, _oracle_ref(P, pos, vel))
+    s.close()
+
+
+def test_kernel_variants_agree(monkeypatch):
+    """The row-staged sweeps + onesweep sort (default) and the first-generation warp-tile sweeps + three-kernel radix
+    passes (SPH_SWEEP=warp, SPH_SORT=classic) build identical sort orders and neighbour lists."""
+    from cuda_sph_b200 import workloads
+    n = 50000
+    params, st = workloads.dam_break(n, 2.5, seed=34)
+    outs = []
+    for sweep, sort in (("rows", "onesweep"), ("warp", "classic")):
+        monkeypatch.setenv("SPH_SWEEP", sweep)
+        monkeypatch.setenv("SPH_SORT", sort)
+        s = _strategy(n, "BOX", params.space_size, params.voxel_size, params.external_force, params.fps)
+        s.upload(st)
+        s.step(1)
+        outs.append((s.download(), s.sorted_ids(), s.neighbour_counts()))
+        s.close()
+    (a, ia, ca), (b, ib, cb) = outs
+    assert np.array_equal(ia, ib) and np.array_equal(ca, cb)
+    # identical neighbour lists; the force pair sums run in list order in both, but the warp-tile density reduces 32
+    # partial sums by shuffles while the row-staged one adds in list order: agreement to fp32 rounding, not bitwise
+    assert max_rel(a.density, b.density) < 1e-5
+    assert vec_rel(a.position, b.position) < 1e-5
+
+
+def test_reference_pr1_workload_100_steps():
+    """BASELINE configs[0]: box enclosure, 4 096 particles, 100 steps driven like sim/src/main.py (StateGenerator +
+    Saver); the engine must conserve particles, keep the frame files readable by Loader and track the oracle's
+    dead-particle count over the first steps."""
+    import tempfile
+    from cuda_sph_b200 import config
+    from cuda_sph_b200.serializer import Loader, Saver
+    from cuda_sph_b200.state_generator import StateGenerator
+    from oracle import oracle as orc
+    orc.set_exact_pow(False)
+    n = 4096
+    params = config.box_params(n, duration=5, fps=20)            # 100 frames
+    start = config.start_state_box_wall(n, params.space_size, seed=35)
+    with tempfile.TemporaryDirectory() as tmp:
+        saver = Saver("out", params, root=tmp, asynchronous=True)
+        gen = StateGenerator(start, params, config.constants("BOX"))
+        P = orc.OracleParams(n=n, space=tuple(params.space_size), dt=1 / params.fps)
+        pos, vel = start.position, start.velocity
+        frames = 0
+        for k, state in enumerate(gen):
+            saver.save_next_state(state)
+            frames += 1
+            if k < 2:
+                r = orc.step(P, pos, vel, light=True)
+                pos, vel = r.position, r.velocity
+                assert np.array_equal(np.isfinite(state.position).all(axis=1), np.isfinite(pos).all(axis=1))
+            assert state.position.shape == (n, 3) and state.position.dtype == np.float64
+        saver.close()
+        assert frames == 100
+        loader = Loader("out", root=tmp)
+        last = loader.load_simulation_state(99)
+        assert last.position.shape == (n, 3)
+        assert loader.load_simulation_parameters().particle_count == n
+
+
+def test_pipe_4m_single_step_properties():
+    """BASELINE configs[2] size: six-segment pipe, 4M particles, one step: permutation / order / range invariants."""
+    from cuda_sph_b200 import workloads
+    n = 1 << 22
+    params, st = workloads.pipe_flow(n, seed=36)
+    table = params.pipe.to_numpy()
+    s = _strategy(n, "PIPE", params.space_size, params.voxel_size, params.external_force, params.fps, table)
+    s.upload(st)
+    s.step(1)
+    keys, ids, cnt = s.keys(), s.sorted_ids(), s.neighbour_counts()
+    assert np.array_equal(np.sort(ids), np.arange(n, dtype=np.int32))
+    assert np.array_equal(ids, np.lexsort((np.arange(n), keys)).astype(np.int32))
+    assert cnt.min() >= 1 and cnt.max() <= 32
+    out = s.download()
+    assert np.isfinite(out.density).all() and (out.density > 0).all()
     s.close()
