@@ -108,6 +108,7 @@ def run(args, rank, world, local_rank):
     bt = torch.tensor([acc[k_] for k_ in keys_], device=dev, dtype=torch.float64)
     dist.all_reduce(bt, op=dist.ReduceOp.MAX)
     breakdown = {k_: float(v_) for k_, v_ in zip(keys_, bt.tolist())}
+    stt = run_.check()
     # ---- e2e: every step starts from HOST buffers (fp64, pinned) and ends in them: H2D of the rank's owned particles,
     #      exchange + step, D2H of the owned region; wall clock, max over ranks ----
     k0 = int(snap[3][0].item())
@@ -142,7 +143,7 @@ def run(args, rank, world, local_rank):
            "api": "per rank: pinned fp64 (N_own,3) position/velocity -> device, NativeSlabRunner.step(1), owned region -> "
                   "pinned fp64 host (bytes are rank 0's)"}
     restore()
-    stt = run_.check()
+    run_.check()
     stats = torch.tensor([stt["ghosts"], stt["hwm"], stt["live"]], device=dev, dtype=torch.float64)
     allstats = [torch.empty_like(stats) for _ in range(world)]
     dist.all_gather(allstats, stats)

@@ -229,6 +229,19 @@ __device__ __forceinline__ bool own_cell_matches(const GridDesc &g, const float4
     return cell_of(g, p.x, p.y, p.z, vx, vy, vz) && vx == cx && vy == cy && vz == cz;
 }
 
+__device__ __noinline__ float sparse_density(const StepConsts &c, const float4 *rows, const uint16_t *lrow, int k,
+                                             int self, float4 p) {
+    float dens = 0.f;
+    for (int i = 0; i < k; ++i) {
+        const int slot = lrow[i];
+        if (slot == self) continue;
+        const float4 cj = rows[slot];
+        const float dx = p.x - cj.x, dy = p.y - cj.y, dz = p.z - cj.z;
+        dens += poly6_term(c, fmaf(dz, dz, fmaf(dy, dy, dx * dx)), p.x, p.y, p.z, cj.x, cj.y, cj.z);
+    }
+    return dens;
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // density_kernel (voxel_kernels.py:108-132) + neighbour lists
 // ---------------------------------------------------------------------------------------------------------------------
@@ -354,8 +367,14 @@ density_rows_kernel(const SweepArgs a, const GridDesc g, const StepConsts c) {
                     const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
                     if (r2 > c.h2_lo && !in_range_exact(pj.x, pj.y, pj.z, cj.x, cj.y, cj.z, c.r2_max)) continue;
                     lrow[k++] = (uint16_t)slot;
-                    if (slot != selfj) dens += poly6_term(c, r2, pj.x, pj.y, pj.z, cj.x, cj.y, cj.z);
+                    if (slot != selfj) {
+                        const float d = c.h2 - r2;
+                        dens = fmaf(d * d, d, dens);
+                    }
                 }
+                // a sparse particle's density can hinge on one neighbour at the cut-off, where h^2 - r^2 cancels in fp32:
+                // redo the few terms with the fp64 r^2 (never taken by capped lists, where such a term is negligible)
+                if (k <= 8) dens = sparse_density(c, sm.rows, lrow, k, selfj, pj);
                 uint8_t cflag = (uint8_t)k;
                 if (k < kMaxNeighbours && kept >= RB_KEEP) {
                     // the scan stopped on its budget and too many band candidates were rejected: redo exactly

@@ -297,6 +297,52 @@ class GpuSlabRunner(SlabRunner):
             pass
 
 
+def plan_capacities(col_hist, bounds: Sequence[int], rank: int, n_global: int, pipe_mode: bool, *,
+                    own_slack: float = 1.08, ghost_slack: float = 1.4, migrant_frac: float = 0.02,
+                    far_frac: float = 0.005) -> dict:
+    """Slot and block capacities of rank `rank` for the native exchange, derived from the GLOBAL column histogram of the
+    start state so that every rank computes the same block sizes: the block rank a sends to rank b has the size of the
+    block b sends to a (an all_to_all with static split sizes needs that).
+
+    cap_m[r] / cap_g[r]: migrant / ghost records in the block exchanged with rank r.  Adjacent ranks get
+    ghost_slack x (their two boundary columns) ghosts and migrant_frac x (particles per rank) migrants; the others
+    far_frac x (particles per rank) migrants for the rare long jump (in PIPE mode the last <-> first pair carries the
+    outlet -> inlet recycle and gets a quarter of a rank); the block to oneself holds the ghosts a rank keeps of its own
+    emigrants.  own_cap: owned region (own_slack x the fullest rank); capacity: owned + ghost region."""
+    world = len(bounds) - 1
+    hist = np.asarray(col_hist, np.int64)
+    assert len(hist) == bounds[-1] and bounds[0] == 0
+    own = [int(hist[bounds[r]:bounds[r + 1]].sum()) for r in range(world)]
+    per_rank = max(max(own), n_global // world)
+    m_adj = int(migrant_frac * per_rank) + 4096
+
+    def band(r, side):   # particles rank r sends as ghosts to its left (0) / right (1) neighbour at the start
+        lo, hi = bounds[r], bounds[r + 1]
+        return int(hist[lo:lo + HALO].sum()) if side == 0 else int(hist[max(hi - HALO, lo):hi].sum())
+
+    def caps(a, b):      # block a -> b, symmetric in (a, b)
+        if a == b:       # ghosts for oneself: emigrants that stop inside the neighbour's boundary band (most do)
+            return 0, 2 * m_adj
+        a, b = min(a, b), max(a, b)
+        wrap = pipe_mode and a == 0 and b == world - 1
+        if b - a == 1:
+            m, g = m_adj, int(ghost_slack * max(band(a, 1), band(b, 0))) + 4096
+        else:
+            m, g = int(far_frac * per_rank) + 2048, 1024
+        if wrap:
+            m = max(m, per_rank // 4)
+        return m, g
+
+    cap_m = np.asarray([caps(rank, r)[0] for r in range(world)], np.int32)
+    cap_g = np.asarray([caps(rank, r)[1] for r in range(world)], np.int32)
+    # the ghost REGION is sized for the expected halo (the blocks carry more slack: they are only wire volume)
+    expected = sum(band(rank + d, 1 if d < 0 else 0) for d in (-1, 1) if 0 <= rank + d < world)
+    ghost_cap = int(1.4 * expected) + 2 * m_adj + 8192
+    own_cap = int(own_slack * per_rank) + 8192
+    return {"cap_m": cap_m, "cap_g": cap_g, "own_cap": own_cap, "ghost_cap": ghost_cap,
+            "capacity": own_cap + ghost_cap, "per_rank": per_rank}
+
+
 class NativeSlabRunner:
     """x-slab runner on the native exchange path of libsph_b200.so (csrc/slab_exchange.cuh).
 
@@ -331,39 +377,10 @@ class NativeSlabRunner:
         self.compact_every = int(compact_every)
         pipe_mode = cst.mode.upper() == "PIPE"
 
-        # ---- capacities: every rank derives the same numbers from the global column histogram ----
-        hist = np.asarray(col_hist, np.int64)
-        assert len(hist) == self.n_cols
-        own = [int(hist[self.bounds[r]:self.bounds[r + 1]].sum()) for r in range(self.world)]
-        per_rank = max(max(own), self.n_global // self.world)
-
-        def band(r, side):   # particles rank r sends as ghosts to its left (0) / right (1) neighbour at the start
-            lo, hi = self.bounds[r], self.bounds[r + 1]
-            return int(hist[lo:lo + HALO].sum()) if side == 0 else int(hist[max(hi - HALO, lo):hi].sum())
-
-        def caps(a, b):      # block a -> b (symmetric in a, b)
-            if a == b:   # ghosts for myself: my emigrants that stop inside the neighbour's boundary band (most do)
-                return 0, 2 * (int(migrant_frac * per_rank) + 4096)
-            a, b = min(a, b), max(a, b)
-            wrap = pipe_mode and a == 0 and b == self.world - 1
-            if b - a == 1:
-                g = int(ghost_slack * max(band(a, 1), band(b, 0))) + 4096
-                m = int(migrant_frac * per_rank) + 4096
-                if wrap:
-                    m = max(m, int(0.25 * per_rank))
-                return m, g
-            m = int(far_frac * per_rank) + 2048
-            if wrap:
-                m = max(m, int(0.25 * per_rank))
-            return m, 1024
-
-        cap_m = np.asarray([caps(self.rank, r)[0] for r in range(self.world)], np.int32)
-        cap_g = np.asarray([caps(self.rank, r)[1] for r in range(self.world)], np.int32)
-        # the ghost REGION is sized for the expected halo (the blocks carry more slack: they are only wire volume)
-        expected = sum(max(band(self.rank + d, 1 if d < 0 else 0), 0) for d in (-1, 1) if 0 <= self.rank + d < self.world)
-        ghosts_in = int(1.4 * expected) + 2 * (int(migrant_frac * per_rank) + 4096) + 8192
-        self.own_cap = int(own_slack * per_rank) + 8192
-        self.capacity = self.own_cap + ghosts_in
+        plan = plan_capacities(col_hist, self.bounds, self.rank, self.n_global, pipe_mode, own_slack=own_slack,
+                               ghost_slack=ghost_slack, migrant_frac=migrant_frac, far_frac=far_frac)
+        cap_m, cap_g = plan["cap_m"], plan["cap_g"]
+        self.own_cap, self.capacity = plan["own_cap"], plan["capacity"]
 
         p = _lib.SphParams()
         p.particle_count = int(self.capacity)

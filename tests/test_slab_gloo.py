@@ -140,3 +140,31 @@ def test_column_and_owner_mapping():
     assert col.tolist() == [0, 0, 1, 0, 2, 3, 6, 7, 9, -1, -1, 12]
     assert run.owner_of(col[:9]).tolist() == [0, 0, 0, 0, 0, 1, 1, 2, 2]
     assert run.owner_of(torch.tensor([12])).tolist() == [2]   # clamped
+
+
+@pytest.mark.parametrize("world", [2, 3, 4, 8])
+@pytest.mark.parametrize("pipe_mode", [False, True])
+def test_native_exchange_capacities_are_symmetric(world, pipe_mode):
+    """The native exchange is ONE all_to_all with static split sizes: the block a -> b must be as large as b -> a, and
+    every rank must derive that from the global histogram alone."""
+    from cuda_sph_b200.slab import plan_capacities
+    rng = np.random.default_rng(world)
+    hist = rng.integers(50, 4000, size=64)
+    hist[:6] *= 9                                   # a dam-break-like pile at low x
+    bounds = equal_count_bounds(hist, world)
+    n = int(hist.sum())
+    plans = [plan_capacities(hist, bounds, r, n, pipe_mode) for r in range(world)]
+    for a in range(world):
+        assert plans[a]["cap_m"][a] == 0            # nobody migrates to itself
+        own = int(hist[bounds[a]:bounds[a + 1]].sum())
+        assert plans[a]["own_cap"] >= own and plans[a]["capacity"] > plans[a]["own_cap"]
+        for b in range(world):
+            assert plans[a]["cap_m"][b] == plans[b]["cap_m"][a]
+            assert plans[a]["cap_g"][b] == plans[b]["cap_g"][a]
+        for b in (a - 1, a + 1):                    # a neighbour's two boundary columns fit its ghost block
+            if 0 <= b < world:
+                lo, hi = bounds[b], bounds[b + 1]
+                band = hist[hi - HALO:hi].sum() if b < a else hist[lo:lo + HALO].sum()
+                assert plans[a]["cap_g"][b] >= band
+    if pipe_mode and world > 2:
+        assert plans[0]["cap_m"][world - 1] >= n // world // 4      # outlet -> inlet recycle
