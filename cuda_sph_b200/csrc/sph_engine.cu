@@ -55,6 +55,7 @@ struct SphEngine {
     uint32_t *keys = nullptr, *ka = nullptr, *va = nullptr, *kb = nullptr, *vb = nullptr;
     uint32_t *skeys = nullptr, *sids = nullptr;  // aliases of the final sort buffers
     uint32_t *block_hist = nullptr, *digit_total = nullptr;
+    TilePlan *tile_plans = nullptr;   // one row plan per 128-particle tile of the sweeps (rows_plan_kernel)
     uint32_t *os_ctrl = nullptr;      // onesweep control block (histograms, tickets, look-back status)
     bool onesweep = true;         // SPH_SORT=classic selects the three-kernel passes of radix_sort.cuh
     int ntiles = 0, passes = 0, pass_bits[8]{}, key_bits = 0;
@@ -278,6 +279,7 @@ int sph_create(const SphParams *params, int device, sph_handle_t *out) {
     if (const char *so = getenv("SPH_SORT")) e->onesweep = strcmp(so, "classic") != 0;
     if (e->passes > OS_MAX_PASSES) e->onesweep = false;
     ALLOC(e->os_ctrl, os_ctrl_words(e->passes, (n + OS_TILE - 1) / OS_TILE));
+    ALLOC(e->tile_plans, (n + RB_THREADS - 1) / RB_THREADS);
     ALLOC(e->cell_range, e->cell_capacity);
     if (e->slab) ALLOC(e->gid, n);
     ALLOC(e->stats_d, 4);
@@ -320,7 +322,7 @@ int sph_create(const SphParams *params, int device, sph_handle_t *out) {
                          (int)sizeof(ForceRowsSmem));
     cudaFuncSetAttribute(force_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)sizeof(ForceRowsSmem));
-    e->launches_per_step = 1 + (e->onesweep ? 2 + e->passes : 3 * e->passes) + 1 + 1 + 1 + 1;
+    e->launches_per_step = 1 + (e->onesweep ? 2 + e->passes : 3 * e->passes) + 1 + 1 + 1 + 1 + (e->rows_sweeps ? 1 : 0);
     if (cudaDeviceSynchronize() != cudaSuccess) {
         sph_destroy(e);
         return fail("device error during create");
@@ -335,7 +337,7 @@ int sph_destroy(sph_handle_t e) {
     cudaDeviceSynchronize();
     invalidate_graph(e);
     void *ptrs[] = {e->pos_m, e->vel_m, e->spos, e->svel, e->sforce, e->spress, e->svisc, e->srho, e->nlist, e->ncnt,
-                    e->keys, e->ka, e->va, e->kb, e->vb, e->block_hist, e->digit_total, e->os_ctrl, e->cell_range, e->pipe_d,
+                    e->keys, e->ka, e->va, e->kb, e->vb, e->block_hist, e->digit_total, e->os_ctrl, e->tile_plans, e->cell_range, e->pipe_d,
                     e->rng, e->gid, e->stage, e->stats_d, e->snap_pos, e->snap_vel, e->snap_rng, e->sendbuf, e->recvbuf,
                     e->slab_counters, e->tmp_gid};
     for (void *q : ptrs)
@@ -489,8 +491,10 @@ static int enqueue_step(SphEngine *e, bool timed, int n, int n_own) {
     sa.gid = e->slab ? e->gid : nullptr;
     sa.n = n;
     sa.n_own = n_own;
+    sa.plans = e->tile_plans;
     if (e->rows_sweeps) {
         const int grb = (n + RB_THREADS - 1) / RB_THREADS;
+        rows_plan_kernel<<<(grb + RP_WARPS - 1) / RP_WARPS, RP_WARPS * 32, 0, s>>>(sa, e->grid, e->tile_plans, grb);
         density_rows_kernel<<<grb, RB_THREADS, sizeof(DensityRowsSmem), s>>>(sa, e->grid, e->consts);
         if (timed) cudaEventRecord(e->ev[4], s);
         if (e->spress)

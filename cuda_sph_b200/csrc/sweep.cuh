@@ -35,7 +35,10 @@ constexpr int LIST_STRIDE = 34;      // uint16 entries per list row in shared me
 constexpr unsigned FULL = 0xffffffffu;
 constexpr uint8_t CNT_WALK = 0x80;   // neighbour-count flag: this particle is handled by thread_walk
 
+struct TilePlan;   // sweep_rows.cuh
+
 struct SweepArgs {
+    const TilePlan *plans;   // row-staged sweeps: one plan per 128-particle tile (rows_plan_kernel)
     const float4 *spos;
     const float4 *svel;
     const uint32_t *skeys;
@@ -126,7 +129,7 @@ struct ForceAcc {
 
 // integrating_kernel + collision kernel in fp64 (base_kernels.py:30-98), scatter to the id-ordered master arrays.
 template <bool RECORD_TERMS>
-__device__ __noinline__ void finish_particle(const SweepArgs &a, const StepConsts &c, int t, const float4 pi,
+__device__ __forceinline__ void finish_particle(const SweepArgs &a, const StepConsts &c, int t, const float4 pi,
                                                 const float4 vi, float rho_i, ForceAcc f) {
     const uint32_t id = a.sids[t];
     if ((int)id >= a.n_own) return;              // ghost particle of an x-slab: its owner integrates it

@@ -79,8 +79,6 @@ struct RowPlan {
     int ncell;                  // non-empty cells of the pass
     int fits;
     uint32_t ckey[RB_MAXC];     // key of local cell ci
-    int start13[RB_MAXC];       // sorted index of the first particle of the cell
-    int slot13[RB_MAXC];        // its row slot
 };
 
 struct DensityRowsSmem {
@@ -154,7 +152,6 @@ __device__ __forceinline__ bool rows_setup(const SweepArgs &a, const GridDesc &g
             atomicMin(&plan.row_lo[lane % 9], r.x);
             atomicMax(&plan.row_hi[lane % 9], r.y);
         }
-        if (lane == 13) plan.start13[c] = r.x;
         if (DENSITY && lane < 27) {
             ds->seg[c * 27 + lane] = (uint32_t)r.x;
             ds->seg_cnt[c * 27 + lane] = (uint16_t)min(cnt, 65535);
@@ -202,14 +199,137 @@ __device__ __forceinline__ bool rows_setup(const SweepArgs &a, const GridDesc &g
                 const int cnt = ds->seg_cnt[c * 27 + lane];
                 const int slot0 = plan.row_base[lane % 9] + (start - plan.row_lo[lane % 9]);
                 ds->seg[c * 27 + lane] = cnt ? ((uint32_t)slot0 | ((uint32_t)cnt << 16)) : 0u;
-                if (lane == 13) plan.slot13[c] = slot0;
             }
-        } else if (lane == 0) {
-            plan.slot13[c] = plan.row_base[4] + (plan.start13[c] - plan.row_lo[4]);
         }
     }
     __syncthreads();
     return true;
+}
+
+// ---- row plans, computed once per step for both sweeps ---------------------------------------------------------------------
+// One warp per tile (= the 128 sorted particles of one sweep CTA): the 9 row ranges (min / max over the 27 neighbour
+// ranges of the tile's non-empty cells).  The sweeps then start with one 80-byte load and the TMA copies; without the
+// plan every CTA of both kernels repeats this chain of dependent loads before its first copy can be issued.
+struct TilePlan {
+    int row_lo[9];
+    int row_len[9];
+    int slots;   // sum of row_len
+    int fits;    // slots <= RB_CAP and at most RB_MAXC cells: the whole tile is one pass
+};
+
+constexpr int RP_WARPS = 8;
+
+__global__ void __launch_bounds__(RP_WARPS * 32)
+rows_plan_kernel(const SweepArgs a, const GridDesc g, TilePlan *__restrict__ plans, int ntiles) {
+    const int lane = threadIdx.x & 31;
+    const int tile = blockIdx.x * RP_WARPS + (threadIdx.x >> 5);
+    if (tile >= ntiles) return;
+    const int p0 = tile * RB_THREADS;
+    int lo = INT_MAX, hi = 0;   // lanes 0..8: row `lane`
+    int ncell = 0;
+    for (int chunk = 0; chunk < RB_THREADS / 32; ++chunk) {
+        const int t = p0 + chunk * 32 + lane;
+        const uint32_t key = (t < a.n) ? a.skeys[t] : (uint32_t)g.ncells;
+        const bool live = key != (uint32_t)g.ncells;
+        const bool first = live && ((chunk == 0 && lane == 0) || a.skeys[t - 1] != key);
+        unsigned todo = __ballot_sync(FULL, first);
+        ncell += __popc(todo);
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const uint32_t ckey = __shfl_sync(FULL, key, src);
+            int cx, cy, cz;
+            decode_cell(g, ckey, cx, cy, cz);
+            int2 r = make_int2(0, 0);
+            if (lane < 27) r = neighbour_range(a, g, lane, cx, cy, cz);
+            // rows are (dy, dz) = lane % 9; the three dx cells of a row sit in lanes r, r + 9, r + 18
+            int l3 = (r.y > r.x) ? r.x : INT_MAX, h3 = (r.y > r.x) ? r.y : 0;
+            const int l9 = __shfl_down_sync(FULL, l3, 9), h9 = __shfl_down_sync(FULL, h3, 9);
+            const int l18 = __shfl_down_sync(FULL, l3, 18), h18 = __shfl_down_sync(FULL, h3, 18);
+            if (lane < 9) {
+                lo = min(lo, min(l3, min(l9, l18)));
+                hi = max(hi, max(h3, max(h9, h18)));
+            }
+        }
+    }
+    const int len = (lane < 9) ? max(hi - lo, 0) : 0;
+    int sum = len;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(FULL, sum, o);
+    TilePlan &tp = plans[tile];
+    if (lane < 9) {
+        tp.row_lo[lane] = (len > 0) ? lo : 0;
+        tp.row_len[lane] = len;
+    }
+    if (lane == 0) {
+        tp.slots = sum;
+        tp.fits = (sum <= RB_CAP && ncell <= RB_MAXC) ? 1 : 0;
+    }
+}
+
+// Setup of the whole-tile pass from its TilePlan (tp.fits must hold).  The TMA copies are issued first; the density
+// sweep's per-cell segment tables are built while the rows are in flight.  ci: local cell index (density only).
+template <bool DENSITY>
+__device__ __forceinline__ void rows_setup_planned(const SweepArgs &a, const GridDesc &g, RowPlan &plan,
+                                                   const TilePlan &tp, float4 *rows_a, float4 *rows_b,
+                                                   DensityRowsSmem *ds, int nb, int t, uint32_t key, bool live,
+                                                   int &ci) {
+    const int j = threadIdx.x, lane = j & 31, warp = j >> 5;
+    if (warp == 0) {
+        const int len = (lane < 9) ? tp.row_len[lane] : 0;
+        const int lo = (lane < 9) ? tp.row_lo[lane] : 0;
+        int inc = len;
+#pragma unroll
+        for (int o = 1; o < 16; o <<= 1) {
+            const int u = __shfl_up_sync(FULL, inc, o);
+            if (lane >= o) inc += u;
+        }
+        const int slots = __shfl_sync(FULL, inc, 8);
+        if (lane < 9) {
+            plan.row_base[lane] = inc - len;
+            plan.row_lo[lane] = lo;
+        }
+        if (lane == 0) {
+            plan.row_base[9] = slots;
+            fence_proxy_async();
+            mbar_expect_tx(&plan.mbar, (uint32_t)slots * (DENSITY ? 16u : 32u));
+        }
+        __syncwarp();
+        if (lane < 9 && len > 0) {
+            bulk_g2s(&rows_a[inc - len], &a.spos[lo], (uint32_t)len * 16u, &plan.mbar);
+            if (!DENSITY) bulk_g2s(&rows_b[inc - len], &a.svel[lo], (uint32_t)len * 16u, &plan.mbar);
+        }
+    }
+    if (DENSITY) {
+        // local cells of the tile and their 27 segments (as row slots)
+        const bool mine = live && j < nb;
+        bool first = false;
+        if (mine) first = (j == 0) || (a.skeys[t - 1] != key);
+        const unsigned bal = __ballot_sync(FULL, first);
+        if (lane == 0) plan.wcount[warp] = __popc(bal);
+        __syncthreads();   // also publishes row_lo / row_base
+        int off = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < RB_WARPS; ++w) {
+            const int c = plan.wcount[w];
+            if (w < warp) off += c;
+            total += c;
+        }
+        ci = off + __popc(bal & lanemask_le_()) - 1;
+        if (first) plan.ckey[ci] = key;
+        __syncthreads();
+        for (int c = warp; c < total; c += RB_WARPS) {
+            int cx, cy, cz;
+            decode_cell(g, plan.ckey[c], cx, cy, cz);
+            if (lane < 27) {
+                const int2 r = neighbour_range(a, g, lane, cx, cy, cz);
+                const int cnt = min(r.y - r.x, 65535);
+                const int slot0 = plan.row_base[lane % 9] + (r.x - plan.row_lo[lane % 9]);
+                ds->seg[c * 27 + lane] = cnt > 0 ? ((uint32_t)slot0 | ((uint32_t)cnt << 16)) : 0u;
+            }
+        }
+    }
+    __syncthreads();
 }
 
 // lk + 2 if r < lim else lk: one FSETP + one predicated add (the list offset advances only on a hit)
@@ -290,11 +410,18 @@ density_rows_kernel(const SweepArgs a, const GridDesc g, const StepConsts c) {
     }
 
     uint32_t parity = 0;
+    const bool tp_fits = g.aligned && a.plans[blockIdx.x].fits != 0;
     int pass = g.aligned ? -1 : 4;   // -1: whole CTA; 0..3: one warp's particles; 4: no staging at all (everyone walks)
     int j0 = 0, j1 = nb;
     while (pass < 4) {
         int ci = 0;
-        const bool ok = rows_setup<true>(a, g, plan, sm.rows, nullptr, &sm, j0, j1, t, key, live, ci);
+        bool ok;
+        if (pass < 0) {   // whole tile: planned by rows_plan_kernel, or known not to fit
+            ok = tp_fits;
+            if (ok) rows_setup_planned<true>(a, g, plan, a.plans[blockIdx.x], sm.rows, nullptr, &sm, nb, t, key, live, ci);
+        } else {
+            ok = rows_setup<true>(a, g, plan, sm.rows, nullptr, &sm, j0, j1, t, key, live, ci);
+        }
         const bool in_pass = live && want && j >= j0 && j < j1;
         if (ok) {
             while (!mbar_try_wait(&plan.mbar, parity)) {
@@ -307,7 +434,7 @@ density_rows_kernel(const SweepArgs a, const GridDesc g, const StepConsts c) {
                 // governs the scan length, was measured slower: lanes of different cells diverge at every segment.)
                 const int jj = j;
                 const int tj = t;
-                const int selfj = plan.slot13[ci] + (t - plan.start13[ci]);
+                const int selfj = plan.row_base[4] + (t - plan.row_lo[4]);   // row 4 = (dy, dz) = (0, 0): the tile's own cells
                 const float4 pj = pi;
                 uint16_t *const lrow = sm.list + jj * RB_LSTRIDE;
                 // ---- scan: walk the cell's 27 segments in reference order over the staged rows, keep the first
@@ -452,10 +579,8 @@ force_rows_kernel(const SweepArgs a, const GridDesc g, const StepConsts c) {
         mbar_init(&plan.mbar, 1);
         fence_mbar_init();
     }
-    if (j < nb && !live)   // dead particle: F = external force, rho = 0 (reference NaN semantics carry on)
-        finish_particle<RECORD>(a, c, t, a.spos[t], a.svel[t], a.srho[t], ForceAcc());
     __syncthreads();
-    if (__syncthreads_count(live) == 0) return;
+    const bool any_live = __syncthreads_count(live) != 0;
 
     int cx = 0, cy = 0, cz = 0, my_cnt = 0;
     bool want = false, walk = false;
@@ -470,31 +595,53 @@ force_rows_kernel(const SweepArgs a, const GridDesc g, const StepConsts c) {
             rho_i = a.srho[t];
         }
     }
+    // dead particle: F = external force, rho = 0 (reference NaN semantics carry on); finished in the first trip
+    bool dead_todo = j < nb && !live;
 
     uint32_t parity = 0;
-    int pass = g.aligned ? -1 : 4;
+    const bool tp_fits = g.aligned && any_live && a.plans[blockIdx.x].fits != 0;
+    // -1: whole tile; 0..3: one warp's particles; 4: no staging (Q2 grid: everyone walks; or nothing alive)
+    int pass = (g.aligned && any_live) ? -1 : 4;
     int j0 = 0, j1 = nb;
-    while (pass < 4) {
-        int ci = 0;
-        const bool ok = rows_setup<false>(a, g, plan, sm.rpos, sm.rvel, nullptr, j0, j1, t, key, live, ci);
-        const bool in_pass = live && want && j >= j0 && j < j1;
-        if (ok) {
-            // the lists travel while the rows land
-            uint4 e[4];
-            const uint4 *lg = reinterpret_cast<const uint4 *>(a.nlist + (size_t)t * 32);
-            if (in_pass && !walk) {
+    for (;;) {
+        // every path that completes a particle funnels into the ONE finish_particle call at the bottom of the trip
+        ForceAcc f;
+        float4 pi = make_float4(0.f, 0.f, 0.f, 0.f), vi = pi;
+        float rho_f = rho_i;
+        bool fin = false, need_walk = false;
+        if (dead_todo) {
+            pi = a.spos[t];
+            vi = a.svel[t];
+            rho_f = a.srho[t];
+            fin = true;
+            dead_todo = false;
+        }
+        if (pass < 4) {
+            int ci = 0;
+            bool ok;
+            if (pass < 0) {
+                ok = tp_fits;
+                if (ok)
+                    rows_setup_planned<false>(a, g, plan, a.plans[blockIdx.x], sm.rpos, sm.rvel, nullptr, nb, t, key, live,
+                                              ci);
+            } else {
+                ok = rows_setup<false>(a, g, plan, sm.rpos, sm.rvel, nullptr, j0, j1, t, key, live, ci);
+            }
+            const bool in_pass = live && want && j >= j0 && j < j1;
+            if (ok) {
+                // the lists travel while the rows land
+                uint4 e[4];
+                const uint4 *lg = reinterpret_cast<const uint4 *>(a.nlist + (size_t)t * 32);
+                if (in_pass && !walk) {
 #pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    if (q * 8 < my_cnt) e[q] = __ldg(&lg[q]);
-            }
-            while (!mbar_try_wait(&plan.mbar, parity)) {
-            }
-            parity ^= 1u;
-            if (in_pass) {
-                float4 pi, vi;
-                ForceAcc f;
-                if (!walk) {
-                    const int self = plan.slot13[ci] + (t - plan.start13[ci]);
+                    for (int q = 0; q < 4; ++q)
+                        if (q * 8 < my_cnt) e[q] = __ldg(&lg[q]);
+                }
+                while (!mbar_try_wait(&plan.mbar, parity)) {
+                }
+                parity ^= 1u;
+                if (in_pass && !walk) {
+                    const int self = plan.row_base[4] + (t - plan.row_lo[4]);
                     pi = sm.rpos[self];
                     vi = sm.rvel[self];
                     const float a_i = pi.w;
@@ -510,38 +657,33 @@ force_rows_kernel(const SweepArgs a, const GridDesc g, const StepConsts c) {
                             }
                         }
                     }
-                } else {
-                    pi = a.spos[t];
-                    vi = a.svel[t];
-                    float dens = 0.f;
-                    thread_walk<true>(a, g, c, t, pi, vi, pressure_coeff(c, rho_i), dens, f);
+                    fin = true;
+                } else if (in_pass) {
+                    need_walk = true;
                 }
-                finish_particle<RECORD>(a, c, t, pi, vi, rho_i, f);
+            } else if (pass >= 0 && in_pass) {
+                need_walk = true;   // a 32-particle pass that still does not fit
             }
-        } else if (pass >= 0) {
-            if (in_pass) {
-                const float4 pi = a.spos[t], vi = a.svel[t];
-                ForceAcc f;
-                float dens = 0.f;
-                thread_walk<true>(a, g, c, t, pi, vi, pressure_coeff(c, rho_i), dens, f);
-                finish_particle<RECORD>(a, c, t, pi, vi, rho_i, f);
-            }
+        } else if (!g.aligned && live && want) {
+            need_walk = true;       // Q2 grid
         }
-        if (ok && pass < 0) break;
+        if (need_walk) {   // exact one-thread walk over global memory (rare)
+            ForceAcc fw;
+            float dens = 0.f;
+            pi = a.spos[t];
+            vi = a.svel[t];
+            thread_walk<true>(a, g, c, t, pi, vi, pressure_coeff(c, rho_i), dens, fw);
+            f = fw;
+            fin = true;
+        }
+        if (fin) finish_particle<RECORD>(a, c, t, pi, vi, rho_f, f);
+
+        if (pass >= 4 || (pass < 0 && tp_fits)) break;
         ++pass;
         if (pass * 32 >= nb) break;
         j0 = pass * 32;
         j1 = min(nb, j0 + 32);
         __syncthreads();
-    }
-    if (pass == 4 && !g.aligned) {
-        if (live && want) {
-            const float4 pi = a.spos[t], vi = a.svel[t];
-            ForceAcc f;
-            float dens = 0.f;
-            thread_walk<true>(a, g, c, t, pi, vi, pressure_coeff(c, rho_i), dens, f);
-            finish_particle<RECORD>(a, c, t, pi, vi, rho_i, f);
-        }
     }
 }
 
