@@ -483,20 +483,50 @@ density_rows_kernel(const SweepArgs a, const GridDesc g, const StepConsts c) {
 #undef SPH_TEST_CANDIDATE
                 }
                 const int kept = (lk >> 1) - jj * RB_LSTRIDE;   // <= RB_KEEP + 1
-                // ---- exact pass: fp64 predicate inside the rounding band, first 32 accepted stay (compacted in place),
-                //      poly6 density in list order ----
-                int k = 0;
+                // ---- second pass over the kept candidates: poly6 density in list order + the fp64 predicate ----
+                int k = min(kept, kMaxNeighbours);
                 float dens = 0.f;
-                for (int i = 0; i < kept && k < kMaxNeighbours; ++i) {
-                    const int slot = lrow[i];
-                    const float4 cj = sm.rows[slot];
-                    const float dx = pj.x - cj.x, dy = pj.y - cj.y, dz = pj.z - cj.z;
-                    const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-                    if (r2 > c.h2_lo && !in_range_exact(pj.x, pj.y, pj.z, cj.x, cj.y, cj.z, c.r2_max)) continue;
-                    lrow[k++] = (uint16_t)slot;
-                    if (slot != selfj) {
+                bool band = false;
+                // common case: no kept candidate inside the rounding band -> the list is final as it stands; four
+                // candidates per trip (loads first), poly6 sum over the first 32 in list order
+#pragma unroll 1
+                for (int i = 0; i < k; i += 4) {
+                    float4 cj[4];
+                    int sl[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) sl[u] = lrow[min(i + u, k - 1)];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) cj[u] = sm.rows[sl[u]];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const float dx = pj.x - cj[u].x, dy = pj.y - cj[u].y, dz = pj.z - cj[u].z;
+                        const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                        band = band || r2 > c.h2_lo;
                         const float d = c.h2 - r2;
-                        dens = fmaf(d * d, d, dens);
+                        const float w = (i + u < k && sl[u] != selfj) ? d * d * d : 0.f;
+                        dens += w;
+                    }
+                }
+                for (int i = k; i < kept; ++i) {   // spares beyond the 32nd: only matter if something gets rejected
+                    const float4 cj = sm.rows[lrow[i]];
+                    const float dx = pj.x - cj.x, dy = pj.y - cj.y, dz = pj.z - cj.z;
+                    band = band || fmaf(dz, dz, fmaf(dy, dy, dx * dx)) > c.h2_lo;
+                }
+                if (band) {
+                    // rare: fp64 predicate for the candidates inside the band, first 32 accepted stay (compacted in place)
+                    k = 0;
+                    dens = 0.f;
+                    for (int i = 0; i < kept && k < kMaxNeighbours; ++i) {
+                        const int slot = lrow[i];
+                        const float4 cj = sm.rows[slot];
+                        const float dx = pj.x - cj.x, dy = pj.y - cj.y, dz = pj.z - cj.z;
+                        const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                        if (r2 > c.h2_lo && !in_range_exact(pj.x, pj.y, pj.z, cj.x, cj.y, cj.z, c.r2_max)) continue;
+                        lrow[k++] = (uint16_t)slot;
+                        if (slot != selfj) {
+                            const float d = c.h2 - r2;
+                            dens += d * d * d;
+                        }
                     }
                 }
                 // a sparse particle's density can hinge on one neighbour at the cut-off, where h^2 - r^2 cancels in fp32:
