@@ -15,7 +15,7 @@ import torch.distributed as dist
 
 def run(args, rank, world, local_rank):
     import bench
-    from .slab import NativeSlabRunner, equal_count_bounds
+    from .slab import NativeSlabRunner, balanced_bounds
     from .strategy import B200SPHStrategy, SphConstants
 
     name = args.workload or "box32m"
@@ -25,7 +25,7 @@ def run(args, rank, world, local_rank):
     n_cols = int(np.ceil(params.space_size[0] / voxel_x))
     cols = np.clip((st.position[:, 0] / voxel_x).astype(np.int64), 0, n_cols - 1)
     hist = np.bincount(cols, minlength=n_cols)
-    bounds = equal_count_bounds(hist, world)
+    bounds = balanced_bounds(hist, world)
     own = int(hist[bounds[rank]:bounds[rank + 1]].sum())
     capacity = int(1.35 * max(own, n // world)) + 6 * int(hist.max()) + 4096
     window = args.window

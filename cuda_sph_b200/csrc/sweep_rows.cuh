@@ -22,7 +22,7 @@
 //           instructions per pair, no reductions, list order == the reference's summation order; fp64 integrate +
 //           collide epilogue and scatter to the id-ordered master arrays (finish_particle, sweep.cuh).
 // Both kernels derive the row layout from (sorted keys, cell table) with the same code, so a slot means the same thing
-// in both.  A CTA whose rows do not fit shared memory falls back to four 32-particle passes; a pass that still does
+// in both.  A CTA whose rows do not fit shared memory falls back to 32-particle passes (one per warp); a pass that still does
 // not fit, particles whose own cell differs from their sort cell (aliased keys, reference quirk Q5), grids whose
 // trunc and ceil dims differ (Q2) and particles with a rejected band candidate take the plain one-thread walk of
 // sweep.cuh over global memory (exact, slow, rare).
@@ -31,10 +31,15 @@
 
 namespace sph {
 
-constexpr int RB_THREADS = 128;   // threads == particles per CTA
+#ifndef SPH_RB_THREADS
+#define SPH_RB_THREADS 128   // 256 was measured slower on both sweeps (density 0.49 vs 0.42 ms, force 0.21 vs 0.20 ms at 2^20)
+#endif
+constexpr int RB_THREADS = SPH_RB_THREADS;   // threads == particles per CTA (a tile)
 constexpr int RB_WARPS = RB_THREADS / 32;
-constexpr int RB_CAP = 2048;      // row slots per CTA pass (candidates staged in shared memory)
-constexpr int RB_MAXC = 64;       // non-empty cells per CTA pass
+constexpr int RB_CAP = RB_THREADS == 128 ? 2048 : 3328;   // row slots per CTA pass (candidates staged in shared memory)
+constexpr int RB_MAXC = RB_THREADS / 2;                   // non-empty cells per CTA pass
+constexpr int RB_DENSITY_CTAS = RB_THREADS == 128 ? 4 : 2;   // CTAs per SM the kernels are sized for
+constexpr int RB_FORCE_CTAS = RB_THREADS == 128 ? 3 : 2;
 constexpr int RB_KEEP = 33;       // superset candidates kept per particle (32 + spares for rejected band candidates)
 constexpr int RB_LSTRIDE = 38;    // uint16 per list row (19 words: conflict-free rows; >= RB_KEEP + 1)
 
@@ -375,7 +380,7 @@ __device__ __forceinline__ void publish_density(const SweepArgs &a, const StepCo
     const_cast<float *>(reinterpret_cast<const float *>(a.svel + t))[3] = c.lap_c / rho;
 }
 
-__global__ void __launch_bounds__(RB_THREADS, 4)
+__global__ void __launch_bounds__(RB_THREADS, RB_DENSITY_CTAS)
 density_rows_kernel(const SweepArgs a, const GridDesc g, const StepConsts c) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     DensityRowsSmem &sm = *reinterpret_cast<DensityRowsSmem *>(smem_raw);
@@ -411,9 +416,10 @@ density_rows_kernel(const SweepArgs a, const GridDesc g, const StepConsts c) {
 
     uint32_t parity = 0;
     const bool tp_fits = g.aligned && a.plans[blockIdx.x].fits != 0;
-    int pass = g.aligned ? -1 : 4;   // -1: whole CTA; 0..3: one warp's particles; 4: no staging at all (everyone walks)
+    // -1: whole CTA; 0..RB_WARPS-1: one warp's particles; RB_WARPS: no staging at all (everyone walks)
+    int pass = g.aligned ? -1 : RB_WARPS;
     int j0 = 0, j1 = nb;
-    while (pass < 4) {
+    while (pass < RB_WARPS) {
         int ci = 0;
         bool ok;
         if (pass < 0) {   // whole tile: planned by rows_plan_kernel, or known not to fit
@@ -579,7 +585,7 @@ density_rows_kernel(const SweepArgs a, const GridDesc g, const StepConsts c) {
         j1 = min(nb, j0 + 32);
         __syncthreads();
     }
-    if (pass == 4 && !g.aligned) {   // Q2 grid: no staging, every particle walks
+    if (pass == RB_WARPS && !g.aligned) {   // Q2 grid: no staging, every particle walks
         if (live && want) {
             ForceAcc dummy;
             float dens = 0.f;
@@ -594,7 +600,7 @@ density_rows_kernel(const SweepArgs a, const GridDesc g, const StepConsts c) {
 // (voxel_kernels.py:135-211, base_kernels.py:30-98), driven by the slot lists of density_rows_kernel.
 // ---------------------------------------------------------------------------------------------------------------------
 template <bool RECORD>
-__global__ void __launch_bounds__(RB_THREADS, 3)
+__global__ void __launch_bounds__(RB_THREADS, RB_FORCE_CTAS)
 force_rows_kernel(const SweepArgs a, const GridDesc g, const StepConsts c) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     ForceRowsSmem &sm = *reinterpret_cast<ForceRowsSmem *>(smem_raw);
@@ -630,8 +636,8 @@ force_rows_kernel(const SweepArgs a, const GridDesc g, const StepConsts c) {
 
     uint32_t parity = 0;
     const bool tp_fits = g.aligned && any_live && a.plans[blockIdx.x].fits != 0;
-    // -1: whole tile; 0..3: one warp's particles; 4: no staging (Q2 grid: everyone walks; or nothing alive)
-    int pass = (g.aligned && any_live) ? -1 : 4;
+    // -1: whole tile; 0..RB_WARPS-1: one warp's particles; RB_WARPS: no staging (Q2 grid: everyone walks; or nothing alive)
+    int pass = (g.aligned && any_live) ? -1 : RB_WARPS;
     int j0 = 0, j1 = nb;
     for (;;) {
         // every path that completes a particle funnels into the ONE finish_particle call at the bottom of the trip
@@ -646,7 +652,7 @@ force_rows_kernel(const SweepArgs a, const GridDesc g, const StepConsts c) {
             fin = true;
             dead_todo = false;
         }
-        if (pass < 4) {
+        if (pass < RB_WARPS) {
             int ci = 0;
             bool ok;
             if (pass < 0) {
@@ -708,7 +714,7 @@ force_rows_kernel(const SweepArgs a, const GridDesc g, const StepConsts c) {
         }
         if (fin) finish_particle<RECORD>(a, c, t, pi, vi, rho_f, f);
 
-        if (pass >= 4 || (pass < 0 && tp_fits)) break;
+        if (pass >= RB_WARPS || (pass < 0 && tp_fits)) break;
         ++pass;
         if (pass * 32 >= nb) break;
         j0 = pass * 32;

@@ -49,6 +49,59 @@ def equal_count_bounds(col_hist: np.ndarray, world: int, min_width: int = HALO) 
     return bounds
 
 
+def balanced_bounds(col_hist: np.ndarray, world: int, ghost_weight: float = 0.6, min_width: int = HALO) -> List[int]:
+    """Column boundaries that balance the WORK of a step rather than the owned count: a rank hashes, sorts and stages its
+    ghosts too (two columns per interior side), so the cost of slab [lo, hi) is
+        sum(hist[lo:hi]) + ghost_weight * (hist[lo - HALO:lo] if lo > 0) + ghost_weight * (hist[hi:hi + HALO] if hi < W).
+    Minimises the maximum cost over ranks (binary search on the bound, greedy sweep).  With whole-column slabs this puts
+    the wider slabs at the domain ends, where there is only one halo."""
+    hist = np.asarray(col_hist, np.float64)
+    w = len(hist)
+    if w < world * min_width:
+        raise ValueError(f"{w} cell columns cannot be split into {world} slabs of >= {min_width} columns")
+    cum = np.concatenate([[0.0], np.cumsum(hist)])
+
+    def cost(lo, hi):
+        c = cum[hi] - cum[lo]
+        if lo > 0:
+            c += ghost_weight * (cum[lo] - cum[max(lo - HALO, 0)])
+        if hi < w:
+            c += ghost_weight * (cum[min(hi + HALO, w)] - cum[hi])
+        return c
+
+    def sweep(limit):
+        bounds, lo = [0], 0
+        for r in range(world):
+            rest = world - 1 - r                      # slabs still to be placed after this one
+            hi_max = w - rest * min_width
+            if r == world - 1:
+                hi = w
+                if cost(lo, hi) > limit:
+                    return None
+            else:
+                hi = lo + min_width
+                if hi > hi_max or cost(lo, hi) > limit:
+                    return None
+                while hi < hi_max and cost(lo, hi + 1) <= limit:
+                    hi += 1
+            bounds.append(hi)
+            lo = hi
+        return bounds
+
+    lo_t, hi_t = 0.0, float(cum[-1]) * (1.0 + 2.0 * ghost_weight) + 1.0
+    best = sweep(hi_t)
+    if best is None:
+        return equal_count_bounds(col_hist, world, min_width)
+    for _ in range(60):
+        mid = 0.5 * (lo_t + hi_t)
+        b = sweep(mid)
+        if b is None:
+            lo_t = mid
+        else:
+            best, hi_t = b, mid
+    return [int(x) for x in best]
+
+
 class SlabRunner:
     """Device-agnostic slab logic.  Sub-classes provide the storage tensors and the local step.
 

@@ -168,3 +168,24 @@ def test_native_exchange_capacities_are_symmetric(world, pipe_mode):
                 assert plans[a]["cap_g"][b] >= band
     if pipe_mode and world > 2:
         assert plans[0]["cap_m"][world - 1] >= n // world // 4      # outlet -> inlet recycle
+
+
+def test_balanced_bounds_puts_wider_slabs_at_the_ends():
+    """Work-balanced boundaries: cost = owned + 0.6 x ghost columns; edge ranks have one halo and get more columns."""
+    from cuda_sph_b200.slab import balanced_bounds
+    hist = np.full(162, 1000)
+    b = balanced_bounds(hist, 8)
+    widths = np.diff(b)
+    assert b[0] == 0 and b[-1] == 162 and widths.min() >= HALO
+    assert widths[0] >= widths[1:-1].max() and widths[-1] >= widths[1:-1].max()
+
+    def cost(lo, hi):
+        return hist[lo:hi].sum() + 0.6 * (hist[max(lo - HALO, 0):lo].sum() + hist[hi:hi + HALO].sum())
+    worst = max(cost(b[r], b[r + 1]) for r in range(8))
+    e = equal_count_bounds(hist, 8)
+    assert worst <= max(cost(e[r], e[r + 1]) for r in range(8))
+    # a dam-break pile: still a valid partition, and never worse than equal counts
+    hist2 = np.zeros(75, np.int64)
+    hist2[:8] = 131072
+    b2 = balanced_bounds(hist2, 4)
+    assert b2[0] == 0 and b2[-1] == 75 and np.diff(b2).min() >= HALO
