@@ -32,14 +32,16 @@
 namespace sph {
 
 #ifndef SPH_RB_THREADS
-#define SPH_RB_THREADS 128   // 256 was measured slower on both sweeps (density 0.49 vs 0.42 ms, force 0.21 vs 0.20 ms at 2^20)
+// measured at 2^20 dam-break (25/cell) / 2^22 box (8/cell), density + force ms:  64: 0.41+0.20 / 1.58+0.76;
+// 128: 0.42+0.20 / 1.40+0.67;  256: 0.49+0.21 / 1.48+0.72
+#define SPH_RB_THREADS 128
 #endif
 constexpr int RB_THREADS = SPH_RB_THREADS;   // threads == particles per CTA (a tile)
 constexpr int RB_WARPS = RB_THREADS / 32;
-constexpr int RB_CAP = RB_THREADS == 128 ? 2048 : 3328;   // row slots per CTA pass (candidates staged in shared memory)
+constexpr int RB_CAP = RB_THREADS == 128 ? 2048 : RB_THREADS == 64 ? 1536 : 3328;   // row slots per CTA pass (candidates staged in shared memory)
 constexpr int RB_MAXC = RB_THREADS / 2;                   // non-empty cells per CTA pass
-constexpr int RB_DENSITY_CTAS = RB_THREADS == 128 ? 4 : 2;   // CTAs per SM the kernels are sized for
-constexpr int RB_FORCE_CTAS = RB_THREADS == 128 ? 3 : 2;
+constexpr int RB_DENSITY_CTAS = RB_THREADS == 128 ? 4 : RB_THREADS == 64 ? 6 : 2;   // CTAs per SM the kernels are sized for
+constexpr int RB_FORCE_CTAS = RB_THREADS == 128 ? 3 : RB_THREADS == 64 ? 4 : 2;
 constexpr int RB_KEEP = 33;       // superset candidates kept per particle (32 + spares for rejected band candidates)
 constexpr int RB_LSTRIDE = 38;    // uint16 per list row (19 words: conflict-free rows; >= RB_KEEP + 1)
 
