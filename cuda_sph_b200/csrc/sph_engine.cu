@@ -44,6 +44,8 @@ struct SphEngine {
     int32_t ceil_dims[3]{}, trunc_dims[3]{};
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    cudaStream_t copy_stream = nullptr;   // second stream of sph_compute_next_state (created on first use)
+    cudaEvent_t ev_copy[3]{};
 
     // master (id order) and sorted (cell order) state
     float4 *pos_m = nullptr, *vel_m = nullptr, *spos = nullptr, *svel = nullptr, *sforce = nullptr;
@@ -345,6 +347,9 @@ int sph_destroy(sph_handle_t e) {
     for (auto &ev : e->ev)
         if (ev) cudaEventDestroy(ev);
     if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
+    if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
+    for (auto &ev : e->ev_copy)
+        if (ev) cudaEventDestroy(ev);
     delete e;
     return 0;
 }
@@ -416,15 +421,18 @@ int sph_download(sph_handle_t e, double *p, double *v, double *r) { return downl
 int sph_download_f32(sph_handle_t e, float *p, float *v, float *r) { return download_impl<float>(e, p, v, r); }
 
 // Enqueue one step on e->stream.  If evs != nullptr, records stage boundaries into e->ev[0..5].
-static int enqueue_step(SphEngine *e, bool timed, int n, int n_own) {
+// Enqueue one step on e->stream; `stages` selects parts of it (1: hash + sort, 2: cell table + reorder + row plans +
+// density sweep, 4: force sweep) so that sph_compute_next_state can interleave them with its host copies.
+static int enqueue_step(SphEngine *e, bool timed, int n, int n_own, int stages = 7) {
     cudaStream_t s = e->stream;
     const int g256 = (n + 255) / 256;
     const int ntiles = (n + RS_TILE - 1) / RS_TILE;
     if (timed) cudaEventRecord(e->ev[0], s);
-    hash_kernel<<<g256, 256, 0, s>>>(e->pos_m, e->keys, n, e->grid);
+    if (stages & 1) hash_kernel<<<g256, 256, 0, s>>>(e->pos_m, e->keys, n, e->grid);
     if (timed) cudaEventRecord(e->ev[1], s);
     // LSD radix sort of (key, id): pass 0 reads keys with implicit iota values
-    if (e->onesweep) {
+    if (!(stages & 1)) {
+    } else if (e->onesweep) {
         const int otiles = (n + OS_TILE - 1) / OS_TILE;
         OsPasses ps{};
         ps.n_passes = e->passes;
@@ -462,15 +470,17 @@ static int enqueue_step(SphEngine *e, bool timed, int n, int n_own) {
         }
     }
     if (timed) cudaEventRecord(e->ev[2], s);
-    cudaMemsetAsync(e->cell_range, 0, sizeof(int2) * ((size_t)e->grid.ncells + 1), s);
     const uint32_t *sids = e->sids;
-    if (e->slab) {   // in-cell order by GLOBAL id (the local index order is arrival order on a slab)
-        uint32_t *fixed = (e->sids == e->va) ? e->vb : e->va;
-        cell_range_kernel<<<g256, 256, 0, s>>>(e->skeys, e->cell_range, n);
-        fix_order_kernel<<<g256, 256, 0, s>>>(e->skeys, e->sids, fixed, e->gid, e->cell_range, n, (uint32_t)e->grid.ncells);
-        sids = fixed;
+    if (e->slab) sids = (e->sids == e->va) ? e->vb : e->va;   // in-cell order repaired below
+    if (stages & 2) {
+        cudaMemsetAsync(e->cell_range, 0, sizeof(int2) * ((size_t)e->grid.ncells + 1), s);
+        if (e->slab) {   // in-cell order by GLOBAL id (the local index order is arrival order on a slab)
+            cell_range_kernel<<<g256, 256, 0, s>>>(e->skeys, e->cell_range, n);
+            fix_order_kernel<<<g256, 256, 0, s>>>(e->skeys, e->sids, const_cast<uint32_t *>(sids), e->gid, e->cell_range, n,
+                                                  (uint32_t)e->grid.ncells);
+        }
+        reorder_kernel<<<g256, 256, 0, s>>>(e->skeys, sids, e->pos_m, e->vel_m, e->spos, e->svel, e->cell_range, n);
     }
-    reorder_kernel<<<g256, 256, 0, s>>>(e->skeys, sids, e->pos_m, e->vel_m, e->spos, e->svel, e->cell_range, n);
     if (timed) cudaEventRecord(e->ev[3], s);
     SweepArgs sa{};
     sa.spos = e->spos;
@@ -494,18 +504,22 @@ static int enqueue_step(SphEngine *e, bool timed, int n, int n_own) {
     sa.plans = e->tile_plans;
     if (e->rows_sweeps) {
         const int grb = (n + RB_THREADS - 1) / RB_THREADS;
-        rows_plan_kernel<<<(grb + RP_WARPS - 1) / RP_WARPS, RP_WARPS * 32, 0, s>>>(sa, e->grid, e->tile_plans, grb);
-        density_rows_kernel<<<grb, RB_THREADS, sizeof(DensityRowsSmem), s>>>(sa, e->grid, e->consts);
+        if (stages & 2) {
+            rows_plan_kernel<<<(grb + RP_WARPS - 1) / RP_WARPS, RP_WARPS * 32, 0, s>>>(sa, e->grid, e->tile_plans, grb);
+            density_rows_kernel<<<grb, RB_THREADS, sizeof(DensityRowsSmem), s>>>(sa, e->grid, e->consts);
+        }
         if (timed) cudaEventRecord(e->ev[4], s);
-        if (e->spress)
+        if (!(stages & 4)) {
+        } else if (e->spress)
             force_rows_kernel<true><<<grb, RB_THREADS, sizeof(ForceRowsSmem), s>>>(sa, e->grid, e->consts);
         else
             force_rows_kernel<false><<<grb, RB_THREADS, sizeof(ForceRowsSmem), s>>>(sa, e->grid, e->consts);
     } else {
         const int gsw = (n + SW_THREADS - 1) / SW_THREADS;
-        density_kernel<<<gsw, SW_THREADS, 0, s>>>(sa, e->grid, e->consts);
+        if (stages & 2) density_kernel<<<gsw, SW_THREADS, 0, s>>>(sa, e->grid, e->consts);
         if (timed) cudaEventRecord(e->ev[4], s);
-        if (e->spress)
+        if (!(stages & 4)) {
+        } else if (e->spress)
             force_kernel<true><<<gsw, SW_THREADS, 0, s>>>(sa, e->grid, e->consts);
         else
             force_kernel<false><<<gsw, SW_THREADS, 0, s>>>(sa, e->grid, e->consts);
@@ -576,11 +590,56 @@ int sph_step_timed(sph_handle_t e, int32_t n_steps, SphTimings *t) {
     return 0;
 }
 
+// The reference-facing call.  Same result as sph_upload + sph_step(1) + sph_download, but the host copies are
+// interleaved with the step on two streams: hash + sort run while the velocities are still on their way in, and the
+// density goes out while the force sweep runs (the copies are PCIe-bound: 104 B per particle against a 0.7 us step).
 int sph_compute_next_state(sph_handle_t e, const double *pos_in, const double *vel_in, double *pos_out,
                            double *vel_out, double *density_out) {
-    if (sph_upload(e, pos_in, vel_in)) return 1;
-    if (sph_step(e, 1)) return 1;
-    return sph_download(e, pos_out, vel_out, density_out);
+    if (!e) return fail("null handle");
+    if (!pos_in || !vel_in) return fail("position / velocity is NULL");
+    if (e->slab) return fail("this handle is in x-slab mode: use sph_slab_step");
+    if (e->p.mode == SPH_MODE_PIPE && !e->pipe_d) return fail("PIPE mode needs sph_set_pipe before stepping");
+    CK(cudaSetDevice(e->device));
+    const size_t n = e->n, vec = 3 * n * sizeof(double);
+    if (ensure_stage(e, 7 * n * sizeof(double))) return 1;
+    if (!e->copy_stream) {
+        CK(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&e->ev_copy[0], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&e->ev_copy[1], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&e->ev_copy[2], cudaEventDisableTiming));
+    }
+    cudaStream_t s = e->stream, c2 = e->copy_stream;
+    double *dpos = (double *)e->stage, *dvel = dpos + 3 * n, *drho = dvel + 3 * n;
+    const int g256 = (e->n + 255) / 256;
+    // the staging buffer may still be in use by earlier work on the main stream
+    CK(cudaEventRecord(e->ev_copy[2], s));
+    CK(cudaStreamWaitEvent(c2, e->ev_copy[2], 0));
+    CK(cudaMemcpyAsync(dpos, pos_in, vec, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(dvel, vel_in, vec, cudaMemcpyHostToDevice, c2));
+    CK(cudaEventRecord(e->ev_copy[0], c2));
+    pack_vec_kernel<double><<<g256, 256, 0, s>>>(dpos, e->pos_m, e->n);
+    if (enqueue_step(e, false, e->n, e->n, 1)) return 1;            // hash + sort need positions only
+    CK(cudaStreamWaitEvent(s, e->ev_copy[0], 0));
+    pack_vec_kernel<double><<<g256, 256, 0, s>>>(dvel, e->vel_m, e->n);
+    if (enqueue_step(e, false, e->n, e->n, 2)) return 1;            // ... density
+    CK(cudaEventRecord(e->ev_copy[1], s));
+    if (density_out) {                                              // rho leaves while the forces are computed
+        CK(cudaStreamWaitEvent(c2, e->ev_copy[1], 0));
+        unsort_scalar_kernel<<<g256, 256, 0, c2>>>(e->srho, e->sids, drho, e->n);
+        CK(cudaMemcpyAsync(density_out, drho, n * sizeof(double), cudaMemcpyDeviceToHost, c2));
+    }
+    if (enqueue_step(e, false, e->n, e->n, 4)) return 1;            // force + integrate + collide
+    unpack_state_kernel<double><<<g256, 256, 0, s>>>(e->pos_m, e->vel_m, pos_out ? dpos : nullptr,
+                                                     vel_out ? dvel : nullptr, (double *)nullptr, e->n);
+    CK(cudaGetLastError());
+    if (pos_out) CK(cudaMemcpyAsync(pos_out, dpos, vec, cudaMemcpyDeviceToHost, s));
+    if (vel_out) CK(cudaMemcpyAsync(vel_out, dvel, vec, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    CK(cudaStreamSynchronize(c2));
+    e->has_state = true;
+    e->steps_done += 1;
+    e->launches += e->launches_per_step + 4;
+    return 0;
 }
 
 int sph_save_state(sph_handle_t e) {

@@ -96,6 +96,23 @@ pack_state_kernel(const T *__restrict__ pos3, const T *__restrict__ vel3, float4
                            0.f);
 }
 
+// one (N,3) host-layout array -> float4 (w = 0)
+template <typename T>
+__global__ void __launch_bounds__(256)
+pack_vec_kernel(const T *__restrict__ src3, float4 *__restrict__ dst, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    dst[i] = make_float4((float)src3[3 * (size_t)i], (float)src3[3 * (size_t)i + 1], (float)src3[3 * (size_t)i + 2], 0.f);
+}
+
+// sorted fp32 scalar (density) -> id-ordered fp64
+__global__ void __launch_bounds__(256)
+unsort_scalar_kernel(const float *__restrict__ sorted, const uint32_t *__restrict__ sids, double *__restrict__ out,
+                     int n) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) out[sids[t]] = (double)sorted[t];
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 unpack_state_kernel(const float4 *__restrict__ pos_m, const float4 *__restrict__ vel_m, T *__restrict__ pos3,
