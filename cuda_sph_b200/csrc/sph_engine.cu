@@ -60,6 +60,7 @@ struct SphEngine {
     TilePlan *tile_plans = nullptr;   // one row plan per 128-particle tile of the sweeps (rows_plan_kernel)
     uint32_t *os_ctrl = nullptr;      // onesweep control block (histograms, tickets, look-back status)
     bool onesweep = true;         // SPH_SORT=classic selects the three-kernel passes of radix_sort.cuh
+    bool sort_lookback = false;   // SPH_SORT=lookback: decoupled look-back passes (one kernel per digit) instead of count + scan
     int ntiles = 0, passes = 0, pass_bits[8]{}, key_bits = 0;
     int2 *cell_range = nullptr;
     // pipe
@@ -278,7 +279,10 @@ int sph_create(const SphParams *params, int device, sph_handle_t *out) {
     ALLOC(e->vb, n);
     ALLOC(e->block_hist, (size_t)RS_RADIX * e->ntiles);
     ALLOC(e->digit_total, RS_RADIX);
-    if (const char *so = getenv("SPH_SORT")) e->onesweep = strcmp(so, "classic") != 0;
+    if (const char *so = getenv("SPH_SORT")) {
+        e->onesweep = strcmp(so, "classic") != 0;
+        e->sort_lookback = strcmp(so, "lookback") == 0;
+    }
     if (e->passes > OS_MAX_PASSES) e->onesweep = false;
     ALLOC(e->os_ctrl, os_ctrl_words(e->passes, (n + OS_TILE - 1) / OS_TILE));
     ALLOC(e->tile_plans, (n + RB_THREADS - 1) / RB_THREADS);
@@ -324,7 +328,8 @@ int sph_create(const SphParams *params, int device, sph_handle_t *out) {
                          (int)sizeof(ForceRowsSmem));
     cudaFuncSetAttribute(force_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)sizeof(ForceRowsSmem));
-    e->launches_per_step = 1 + (e->onesweep ? 2 + e->passes : 3 * e->passes) + 1 + 1 + 1 + 1 + (e->rows_sweeps ? 1 : 0);
+    e->launches_per_step = 1 + (e->onesweep ? 2 + (e->sort_lookback ? 1 : 3) * e->passes : 3 * e->passes) + 1 + 1 + 1 + 1 +
+                           (e->rows_sweeps ? 1 : 0);
     if (cudaDeviceSynchronize() != cudaSuccess) {
         sph_destroy(e);
         return fail("device error during create");
@@ -442,14 +447,25 @@ static int enqueue_step(SphEngine *e, bool timed, int n, int n_own, int stages =
             ps.mask[p] = (1u << e->pass_bits[p]) - 1u;
             shift += e->pass_bits[p];
         }
-        cudaMemsetAsync(e->os_ctrl, 0, sizeof(uint32_t) * os_ctrl_words(e->passes, otiles), s);
+        cudaMemsetAsync(e->os_ctrl, 0,
+                        sizeof(uint32_t) * (e->sort_lookback ? os_ctrl_words(e->passes, otiles)
+                                                             : (size_t)e->passes * OS_RADIX + 8), s);
         os_hist<<<std::min(otiles, 148 * 8), OS_THREADS, 0, s>>>(e->keys, n, ps, e->os_ctrl);
         const uint32_t *kin = e->keys, *vin = nullptr;
+        // per-tile counts live behind the control words of the look-back variant (same buffer, never used together)
+        uint32_t *tile_cnt = e->os_ctrl + (size_t)e->passes * OS_RADIX + 8;
         for (int p = 0; p < e->passes; ++p) {
             uint32_t *kout = (p % 2 == 0) ? e->ka : e->kb;
             uint32_t *vout = (p % 2 == 0) ? e->va : e->vb;
-            os_pass<<<otiles, OS_THREADS, 0, s>>>(kin, vin, kout, vout, n, p, e->passes, ps.shift[p], ps.mask[p], otiles,
-                                                  e->os_ctrl);
+            if (e->sort_lookback) {
+                os_pass<<<otiles, OS_THREADS, 0, s>>>(kin, vin, kout, vout, n, p, e->passes, ps.shift[p], ps.mask[p],
+                                                      otiles, e->os_ctrl);
+            } else {
+                ts_hist<<<otiles, OS_THREADS, 0, s>>>(kin, n, ps.shift[p], ps.mask[p], tile_cnt, otiles);
+                ts_scan<<<OS_RADIX, OS_THREADS, 0, s>>>(tile_cnt, otiles, e->os_ctrl + p * OS_RADIX);
+                ts_scatter<<<otiles, OS_THREADS, 0, s>>>(kin, vin, kout, vout, n, ps.shift[p], ps.mask[p], tile_cnt,
+                                                         otiles);
+            }
             kin = kout;
             vin = vout;
         }
