@@ -241,21 +241,30 @@ rows_plan_kernel(const SweepArgs a, const GridDesc g, TilePlan *__restrict__ pla
         const bool first = live && ((chunk == 0 && lane == 0) || a.skeys[t - 1] != key);
         unsigned todo = __ballot_sync(FULL, first);
         ncell += __popc(todo);
-        while (todo) {
-            const int src = __ffs(todo) - 1;
-            todo &= todo - 1;
-            const uint32_t ckey = __shfl_sync(FULL, key, src);
-            int cx, cy, cz;
-            decode_cell(g, ckey, cx, cy, cz);
-            int2 r = make_int2(0, 0);
-            if (lane < 27) r = neighbour_range(a, g, lane, cx, cy, cz);
-            // rows are (dy, dz) = lane % 9; the three dx cells of a row sit in lanes r, r + 9, r + 18
-            int l3 = (r.y > r.x) ? r.x : INT_MAX, h3 = (r.y > r.x) ? r.y : 0;
-            const int l9 = __shfl_down_sync(FULL, l3, 9), h9 = __shfl_down_sync(FULL, h3, 9);
-            const int l18 = __shfl_down_sync(FULL, l3, 18), h18 = __shfl_down_sync(FULL, h3, 18);
-            if (lane < 9) {
-                lo = min(lo, min(l3, min(l9, l18)));
-                hi = max(hi, max(h3, max(h9, h18)));
+        while (todo) {   // four cells per trip: their range loads are independent, issue them together
+            int2 r[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                r[u] = make_int2(0, 0);
+                if (todo) {
+                    const int src = __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    const uint32_t ckey = __shfl_sync(FULL, key, src);
+                    int cx, cy, cz;
+                    decode_cell(g, ckey, cx, cy, cz);
+                    if (lane < 27) r[u] = neighbour_range(a, g, lane, cx, cy, cz);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                // rows are (dy, dz) = lane % 9; the three dx cells of a row sit in lanes r, r + 9, r + 18
+                const int l3 = (r[u].y > r[u].x) ? r[u].x : INT_MAX, h3 = (r[u].y > r[u].x) ? r[u].y : 0;
+                const int l9 = __shfl_down_sync(FULL, l3, 9), h9 = __shfl_down_sync(FULL, h3, 9);
+                const int l18 = __shfl_down_sync(FULL, l3, 18), h18 = __shfl_down_sync(FULL, h3, 18);
+                if (lane < 9) {
+                    lo = min(lo, min(l3, min(l9, l18)));
+                    hi = max(hi, max(h3, max(h9, h18)));
+                }
             }
         }
     }
@@ -325,14 +334,28 @@ __device__ __forceinline__ void rows_setup_planned(const SweepArgs &a, const Gri
         ci = off + __popc(bal & lanemask_le_()) - 1;
         if (first) plan.ckey[ci] = key;
         __syncthreads();
-        for (int c = warp; c < total; c += RB_WARPS) {
-            int cx, cy, cz;
-            decode_cell(g, plan.ckey[c], cx, cy, cz);
-            if (lane < 27) {
-                const int2 r = neighbour_range(a, g, lane, cx, cy, cz);
-                const int cnt = min(r.y - r.x, 65535);
-                const int slot0 = plan.row_base[lane % 9] + (r.x - plan.row_lo[lane % 9]);
-                ds->seg[c * 27 + lane] = cnt > 0 ? ((uint32_t)slot0 | ((uint32_t)cnt << 16)) : 0u;
+        // four cells per trip: their 27 range loads are independent, so issue them together (a tile of sparse
+        // particles has ~50 cells and this loop would otherwise pay one global round trip per cell)
+        const int rbase = plan.row_base[lane % 9] - plan.row_lo[lane % 9];
+        for (int c0 = warp; c0 < total; c0 += 4 * RB_WARPS) {
+            int2 r[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int c = c0 + u * RB_WARPS;
+                r[u] = make_int2(0, 0);
+                if (c < total && lane < 27) {
+                    int cx, cy, cz;
+                    decode_cell(g, plan.ckey[c], cx, cy, cz);
+                    r[u] = neighbour_range(a, g, lane, cx, cy, cz);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int c = c0 + u * RB_WARPS;
+                if (c < total && lane < 27) {
+                    const int cnt = min(r[u].y - r[u].x, 65535);
+                    ds->seg[c * 27 + lane] = cnt > 0 ? ((uint32_t)(rbase + r[u].x) | ((uint32_t)cnt << 16)) : 0u;
+                }
             }
         }
     }
