@@ -270,6 +270,50 @@ class SlabRunner:
         return int(c.item())
 
 
+class SingleExchangeSlabRunner(SlabRunner):
+    """The protocol of the native path (csrc/slab_exchange.cuh) in torch ops: ghosts AND migrants of a step travel in one
+    exchange, because the sender of a particle knows its final owner o and therefore also which neighbour of o needs it
+    as a ghost (o - 1 if it sits in o's first two columns, o + 1 if in its last two).  Same routing rule, expression
+    for expression, as slab_route_kernel; tests/test_slab_gloo.py runs it over gloo with the oracle as the local step."""
+
+    def route_and_exchange(self) -> None:
+        n = self.n_own
+        dev = self.P.device
+        col = self.columns(self.P[:n, 0])
+        o = torch.where(col >= 0, self.owner_of(col), torch.full_like(col, self.rank))
+        b = torch.tensor(self.bounds, dtype=torch.int64, device=dev)
+        lo, hi = b[o], b[o + 1]
+        leaves = o != self.rank
+        ghost_l = (o > 0) & (col >= lo) & (col < lo + HALO)
+        ghost_r = (o < self.world - 1) & (col >= hi - HALO) & (col < hi)
+        im, il, ir = (torch.nonzero(m).flatten() for m in (leaves, ghost_l, ghost_r))
+        idx = torch.cat([im, il, ir])
+        dest = torch.cat([o[im], o[il] - 1, o[ir] + 1])
+        kind = torch.cat([torch.zeros_like(im), torch.ones_like(il), torch.ones_like(ir)]).to(torch.uint8)
+        rows = torch.cat([self._pack(idx, with_rng=True), kind[:, None]], dim=1)
+        if self.world > 1:
+            got = self._exchange(rows, dest)
+        else:
+            got = rows
+        # the emigrants' slots are closed
+        keep = torch.nonzero(~leaves).flatten()
+        k = len(keep)
+        if k != n:
+            self.P[:k], self.V[:k], self.G[:k] = self.P[keep], self.V[keep], self.G[keep]
+        is_ghost = got[:, -1] == 1
+        mig, gho = got[~is_ghost][:, :-1], got[is_ghost][:, :-1]
+        self.n_own = k + self._unpack(mig, k, with_rng=True)
+        self.n_local = self.n_own + self._unpack(gho, self.n_own, with_rng=False)
+        self.stats["halo_sent"] += int(len(il) + len(ir))
+        self.stats["migrated"] += int(len(im))
+
+    def step(self, n_steps: int = 1) -> None:
+        for _ in range(n_steps):
+            self.route_and_exchange()
+            self._local_step(self.n_own, self.n_local)
+            self.stats["steps"] += 1
+
+
 class _CudaBuffer:
     """Zero-copy view of a raw device pointer for torch.as_tensor (__cuda_array_interface__ v2)."""
 

@@ -13,13 +13,13 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from cuda_sph_b200 import config, workloads
-from cuda_sph_b200.slab import HALO, SlabRunner, equal_count_bounds
+from cuda_sph_b200.slab import HALO, SingleExchangeSlabRunner, SlabRunner, equal_count_bounds
 from oracle import oracle as orc
 from tests.helpers import same
 
 
-class OracleSlabRunner(SlabRunner):
-    """SlabRunner whose local step is the CPU oracle on (owned + ghost) particles."""
+class _OracleStep:
+    """Local step = the CPU oracle on (owned + ghost) particles; mixed into both protocol runners."""
 
     def __init__(self, P: orc.OracleParams, n_global, capacity, n_cols, bounds, pipe_mode):
         super().__init__(n_cols, P.voxel[0], bounds)
@@ -51,6 +51,14 @@ class OracleSlabRunner(SlabRunner):
             self.R[torch.from_numpy(gid[:n_own].astype(np.int64))] = torch.from_numpy(rng[own].view(np.int64))
 
 
+class OracleSlabRunner(_OracleStep, SlabRunner):
+    """Two exchanges per step: halo, local step, migration."""
+
+
+class OracleSingleExchangeRunner(_OracleStep, SingleExchangeSlabRunner):
+    """One exchange per step (the protocol of the native CUDA path): route + exchange, local step."""
+
+
 def _case(mode):
     if mode == "BOX":
         n = 3000
@@ -69,7 +77,7 @@ def _case(mode):
     return n, params, st, P
 
 
-def _worker(rank, world, port, mode, steps, out_path):
+def _worker(rank, world, port, mode, steps, out_path, single_exchange=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
@@ -79,7 +87,8 @@ def _worker(rank, world, port, mode, steps, out_path):
         n_cols = int(np.ceil(params.space_size[0] / params.voxel_size[0]))
         cols = np.clip((st.position[:, 0] / params.voxel_size[0]).astype(np.int64), 0, n_cols - 1)
         bounds = equal_count_bounds(np.bincount(cols, minlength=n_cols), world)
-        run = OracleSlabRunner(P, n, capacity=2 * n, n_cols=n_cols, bounds=bounds, pipe_mode=(mode == "PIPE"))
+        cls = OracleSingleExchangeRunner if single_exchange else OracleSlabRunner
+        run = cls(P, n, capacity=2 * n, n_cols=n_cols, bounds=bounds, pipe_mode=(mode == "PIPE"))
         run.load_global(st.position, st.velocity)
         assert run.count_global() == n
         run.step(steps)
@@ -100,11 +109,12 @@ def _free_port():
         return s.getsockname()[1]
 
 
+@pytest.mark.parametrize("single_exchange", [False, True], ids=["two-exchanges", "single-exchange"])
 @pytest.mark.parametrize("world,mode", [(2, "BOX"), (3, "BOX"), (2, "PIPE")])
-def test_slab_decomposition_matches_single_domain_bitwise(tmp_path, world, mode):
+def test_slab_decomposition_matches_single_domain_bitwise(tmp_path, world, mode, single_exchange):
     steps = 3
     out = str(tmp_path / "slab.npz")
-    mp.spawn(_worker, args=(world, _free_port(), mode, steps, out), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), mode, steps, out, single_exchange), nprocs=world, join=True)
     got = np.load(out)
     # single-domain oracle
     orc.set_exact_pow(False)
