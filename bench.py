@@ -312,17 +312,25 @@ def run_gpu_arm(args):
     stage_bytes = dict(BYTES, sort=sort_bytes(passes))
     stage_gbs = {k_: stage_bytes[k_] * n / (stage_ms[k_] * 1e-3) / 1e9 for k_ in stage_ms}
     dom = max(stage_ms, key=stage_ms.get)
-    traffic = None
+    traffic, issue = None, None
     try:   # measured DRAM bytes per launch of the dominant kernel, from the committed ncu capture of this workload
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(name)
         if tj and tj["particles"] == n and dom in tj:
             traffic = tj[dom]["bytes"]
+            if "warp_inst" in tj[dom]:
+                # second roof, the one that binds: warp instructions per launch (ncu) / live kernel time vs the issue
+                # slots of the chip (148 SMs x 4 schedulers x SM clock)
+                peak_issue = 148 * 4 * 1.965e9
+                rate = tj[dom]["warp_inst"] / (stage_ms[dom] * 1e-3)
+                issue = {"warp_inst_per_launch": tj[dom]["warp_inst"], "achieved_ginst_s": rate / 1e9,
+                         "peak_ginst_s": peak_issue / 1e9, "frac": rate / peak_issue,
+                         "peak_source": "148 SMs x 4 issue slots x 1.965 GHz"}
     except Exception:
         pass
     kname = {"density": "density_rows_kernel", "force": "force_rows_kernel"}.get(dom, dom + "_kernel")
     roofline = {"bound": "hbm", "kernel": kname, "achieved": stage_gbs[dom], "peak": hbm_peak,
                 "unit": "GB/s", "frac": stage_gbs[dom] / hbm_peak, "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": stage_bytes[dom] * n,
+                "algorithmic_bytes_per_launch": stage_bytes[dom] * n, "issue_roofline": issue,
                 "algorithmic_bytes_per_particle": stage_bytes[dom], "kernel_ms": stage_ms[dom],
                 "stages_ms": stage_ms, "stages_gbs": stage_gbs,
                 "step_bytes_per_particle": sum(stage_bytes.values()),
