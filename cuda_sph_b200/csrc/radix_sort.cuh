@@ -1,3 +1,4 @@
+// FIRST-GENERATION sort (SPH_SORT=classic); the engine default is radix_onesweep.cuh.
 // Stable LSD radix sort of (cell key, particle index) pairs -- the device replacement of the reference's host-side
 // numpy structured sort (voxel_sph_strategy.py:81-88).  Stability + values starting as iota give exactly numpy's
 // (voxel_id, particle_id) order.

@@ -1,5 +1,7 @@
-// Neighbour sweeps (sm_100a): density_kernel (+ neighbour lists) and the fused pressure + viscosity + integrate +
-// collide force_kernel.
+// Shared pieces of the neighbour sweeps (pair terms, the fp64 integrate + collide epilogue `finish_particle`, the exact
+// one-thread `thread_walk` fallback) and the FIRST-GENERATION sweeps: density_kernel / force_kernel with per-warp
+// shared-memory tiles.  The engine runs the row-staged sweeps of sweep_rows.cuh by default; these are selected with
+// SPH_SWEEP=warp and kept for A/B measurements (tests/test_gpu_parity.py::test_kernel_variants_agree).
 //
 // Reference semantics (voxel_kernels.py:29-85): a particle's neighbour list is the first 32 candidates (self included)
 // that pass sqrt(r^2) <= INF_R when the <= 27 cells around it are walked with dx outermost and dz innermost and the
