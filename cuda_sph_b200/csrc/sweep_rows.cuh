@@ -283,39 +283,49 @@ rows_plan_kernel(const SweepArgs a, const GridDesc g, TilePlan *__restrict__ pla
     }
 }
 
-// Setup of the whole-tile pass from its TilePlan (tp.fits must hold).  The TMA copies are issued first; the density
-// sweep's per-cell segment tables are built while the rows are in flight.  ci: local cell index (density only).
+// First thing a sweep CTA does (warp 0 only, before any CTA-wide barrier): initialise the mbarrier and, if the tile has a
+// fitting plan, put its TMA row copies in flight -- every other load of the CTA's prologue then overlaps with them.
+template <bool DENSITY>
+__device__ __forceinline__ void rows_issue_planned(const SweepArgs &a, const GridDesc &g, RowPlan &plan,
+                                                   const TilePlan &tp, float4 *rows_a, float4 *rows_b) {
+    const int lane = threadIdx.x & 31;
+    if (lane == 0) {
+        mbar_init(&plan.mbar, 1);
+        fence_mbar_init();
+    }
+    __syncwarp();
+    if (!g.aligned || !tp.fits) return;
+    const int len = (lane < 9) ? tp.row_len[lane] : 0;
+    const int lo = (lane < 9) ? tp.row_lo[lane] : 0;
+    int inc = len;
+#pragma unroll
+    for (int o = 1; o < 16; o <<= 1) {
+        const int u = __shfl_up_sync(FULL, inc, o);
+        if (lane >= o) inc += u;
+    }
+    const int slots = __shfl_sync(FULL, inc, 8);
+    if (lane < 9) {
+        plan.row_base[lane] = inc - len;
+        plan.row_lo[lane] = lo;
+    }
+    if (lane == 0) {
+        plan.row_base[9] = slots;
+        mbar_expect_tx(&plan.mbar, (uint32_t)slots * (DENSITY ? 16u : 32u));
+    }
+    __syncwarp();
+    if (lane < 9 && len > 0) {
+        bulk_g2s(&rows_a[inc - len], &a.spos[lo], (uint32_t)len * 16u, &plan.mbar);
+        if (!DENSITY) bulk_g2s(&rows_b[inc - len], &a.svel[lo], (uint32_t)len * 16u, &plan.mbar);
+    }
+}
+
+// Rest of the whole-tile setup (its TMA copies were issued by rows_issue_planned): the density sweep builds its per-cell
+// segment tables while the rows are in flight.  ci: local cell index (density only).
 template <bool DENSITY>
 __device__ __forceinline__ void rows_setup_planned(const SweepArgs &a, const GridDesc &g, RowPlan &plan,
-                                                   const TilePlan &tp, float4 *rows_a, float4 *rows_b,
                                                    DensityRowsSmem *ds, int nb, int t, uint32_t key, bool live,
                                                    int &ci) {
     const int j = threadIdx.x, lane = j & 31, warp = j >> 5;
-    if (warp == 0) {
-        const int len = (lane < 9) ? tp.row_len[lane] : 0;
-        const int lo = (lane < 9) ? tp.row_lo[lane] : 0;
-        int inc = len;
-#pragma unroll
-        for (int o = 1; o < 16; o <<= 1) {
-            const int u = __shfl_up_sync(FULL, inc, o);
-            if (lane >= o) inc += u;
-        }
-        const int slots = __shfl_sync(FULL, inc, 8);
-        if (lane < 9) {
-            plan.row_base[lane] = inc - len;
-            plan.row_lo[lane] = lo;
-        }
-        if (lane == 0) {
-            plan.row_base[9] = slots;
-            fence_proxy_async();
-            mbar_expect_tx(&plan.mbar, (uint32_t)slots * (DENSITY ? 16u : 32u));
-        }
-        __syncwarp();
-        if (lane < 9 && len > 0) {
-            bulk_g2s(&rows_a[inc - len], &a.spos[lo], (uint32_t)len * 16u, &plan.mbar);
-            if (!DENSITY) bulk_g2s(&rows_b[inc - len], &a.svel[lo], (uint32_t)len * 16u, &plan.mbar);
-        }
-    }
     if (DENSITY) {
         // local cells of the tile and their 27 segments (as row slots)
         const bool mine = live && j < nb;
@@ -416,10 +426,7 @@ density_rows_kernel(const SweepArgs a, const GridDesc g, const StepConsts c) {
     const int nb = min(RB_THREADS, a.n - p0);
     const uint32_t key = (j < nb) ? a.skeys[t] : (uint32_t)g.ncells;
     const bool live = key != (uint32_t)g.ncells;
-    if (j == 0) {
-        mbar_init(&plan.mbar, 1);
-        fence_mbar_init();
-    }
+    if (warp == 0) rows_issue_planned<true>(a, g, plan, a.plans[blockIdx.x], sm.rows, nullptr);
     if (j < 8) sm.rows[RB_CAP + j] = make_float4(1e18f, 1e18f, 1e18f, 0.f);
     if (j < nb && !live) {   // dead particle: no neighbours
         a.srho[t] = 0.f;
@@ -449,7 +456,7 @@ density_rows_kernel(const SweepArgs a, const GridDesc g, const StepConsts c) {
         bool ok;
         if (pass < 0) {   // whole tile: planned by rows_plan_kernel, or known not to fit
             ok = tp_fits;
-            if (ok) rows_setup_planned<true>(a, g, plan, a.plans[blockIdx.x], sm.rows, nullptr, &sm, nb, t, key, live, ci);
+            if (ok) rows_setup_planned<true>(a, g, plan, &sm, nb, t, key, live, ci);
         } else {
             ok = rows_setup<true>(a, g, plan, sm.rows, nullptr, &sm, j0, j1, t, key, live, ci);
         }
@@ -636,10 +643,10 @@ force_rows_kernel(const SweepArgs a, const GridDesc g, const StepConsts c) {
     const int nb = min(RB_THREADS, a.n - p0);
     const uint32_t key = (j < nb) ? a.skeys[t] : (uint32_t)g.ncells;
     const bool live = key != (uint32_t)g.ncells;
-    if (j == 0) {
-        mbar_init(&plan.mbar, 1);
-        fence_mbar_init();
-    }
+    if ((j >> 5) == 0) rows_issue_planned<false>(a, g, plan, a.plans[blockIdx.x], sm.rpos, sm.rvel);
+    // issued before the key arrives (their use depends on it, their address does not)
+    const uint8_t cf_raw = (j < nb) ? a.ncnt[t] : (uint8_t)0;
+    const float rho_raw = (j < nb) ? a.srho[t] : 0.f;
     __syncthreads();
     const bool any_live = __syncthreads_count(live) != 0;
 
@@ -650,10 +657,9 @@ force_rows_kernel(const SweepArgs a, const GridDesc g, const StepConsts c) {
         decode_cell(g, key, cx, cy, cz);
         want = !(cx < g.own_lo || cx >= g.own_hi);   // x-slab: ghost cell, its owner computes the forces
         if (want) {
-            const uint8_t cf = a.ncnt[t];
-            walk = (cf & CNT_WALK) != 0;
-            my_cnt = walk ? 0 : cf;
-            rho_i = a.srho[t];
+            walk = (cf_raw & CNT_WALK) != 0;
+            my_cnt = walk ? 0 : cf_raw;
+            rho_i = rho_raw;
         }
     }
     // dead particle: F = external force, rho = 0 (reference NaN semantics carry on); finished in the first trip
@@ -673,7 +679,7 @@ force_rows_kernel(const SweepArgs a, const GridDesc g, const StepConsts c) {
         if (dead_todo) {
             pi = a.spos[t];
             vi = a.svel[t];
-            rho_f = a.srho[t];
+            rho_f = rho_raw;
             fin = true;
             dead_todo = false;
         }
@@ -682,9 +688,7 @@ force_rows_kernel(const SweepArgs a, const GridDesc g, const StepConsts c) {
             bool ok;
             if (pass < 0) {
                 ok = tp_fits;
-                if (ok)
-                    rows_setup_planned<false>(a, g, plan, a.plans[blockIdx.x], sm.rpos, sm.rvel, nullptr, nb, t, key, live,
-                                              ci);
+                if (ok) rows_setup_planned<false>(a, g, plan, nullptr, nb, t, key, live, ci);
             } else {
                 ok = rows_setup<false>(a, g, plan, sm.rpos, sm.rvel, nullptr, j0, j1, t, key, live, ci);
             }
