@@ -428,7 +428,8 @@ int sph_download_f32(sph_handle_t e, float *p, float *v, float *r) { return down
 // Enqueue one step on e->stream.  If evs != nullptr, records stage boundaries into e->ev[0..5].
 // Enqueue one step on e->stream; `stages` selects parts of it (1: hash + sort, 2: cell table + reorder + row plans +
 // density sweep, 4: force sweep) so that sph_compute_next_state can interleave them with its host copies.
-static int enqueue_step(SphEngine *e, bool timed, int n, int n_own, int stages = 7) {
+// split_vel: the reorder leaves the velocities out and stage 4 starts with their gather (the caller uploads them late).
+static int enqueue_step(SphEngine *e, bool timed, int n, int n_own, int stages = 7, bool split_vel = false) {
     cudaStream_t s = e->stream;
     const int g256 = (n + 255) / 256;
     const int ntiles = (n + RS_TILE - 1) / RS_TILE;
@@ -495,8 +496,12 @@ static int enqueue_step(SphEngine *e, bool timed, int n, int n_own, int stages =
             fix_order_kernel<<<g256, 256, 0, s>>>(e->skeys, e->sids, const_cast<uint32_t *>(sids), e->gid, e->cell_range, n,
                                                   (uint32_t)e->grid.ncells);
         }
-        reorder_kernel<<<g256, 256, 0, s>>>(e->skeys, sids, e->pos_m, e->vel_m, e->spos, e->svel, e->cell_range, n);
+        if (split_vel)
+            reorder_kernel<false><<<g256, 256, 0, s>>>(e->skeys, sids, e->pos_m, e->vel_m, e->spos, e->svel, e->cell_range, n);
+        else
+            reorder_kernel<true><<<g256, 256, 0, s>>>(e->skeys, sids, e->pos_m, e->vel_m, e->spos, e->svel, e->cell_range, n);
     }
+    if ((stages & 4) && split_vel) gather_vel_kernel<<<g256, 256, 0, s>>>(sids, e->vel_m, e->svel, n);
     if (timed) cudaEventRecord(e->ev[3], s);
     SweepArgs sa{};
     sa.spos = e->spos;
@@ -607,8 +612,8 @@ int sph_step_timed(sph_handle_t e, int32_t n_steps, SphTimings *t) {
 }
 
 // The reference-facing call.  Same result as sph_upload + sph_step(1) + sph_download, but the host copies are
-// interleaved with the step on two streams: hash + sort run while the velocities are still on their way in, and the
-// density goes out while the force sweep runs (the copies are PCIe-bound: 104 B per particle against a 0.7 us step).
+// interleaved with the step on two streams: everything up to and including the density sweep needs positions only and
+// runs while the velocities are still on their way in, and the density goes out while the force sweep runs (the copies are PCIe-bound: 104 B per particle against a 0.7 us step).
 int sph_compute_next_state(sph_handle_t e, const double *pos_in, const double *vel_in, double *pos_out,
                            double *vel_out, double *density_out) {
     if (!e) return fail("null handle");
@@ -634,17 +639,18 @@ int sph_compute_next_state(sph_handle_t e, const double *pos_in, const double *v
     CK(cudaMemcpyAsync(dvel, vel_in, vec, cudaMemcpyHostToDevice, c2));
     CK(cudaEventRecord(e->ev_copy[0], c2));
     pack_vec_kernel<double><<<g256, 256, 0, s>>>(dpos, e->pos_m, e->n);
-    if (enqueue_step(e, false, e->n, e->n, 1)) return 1;            // hash + sort need positions only
-    CK(cudaStreamWaitEvent(s, e->ev_copy[0], 0));
-    pack_vec_kernel<double><<<g256, 256, 0, s>>>(dvel, e->vel_m, e->n);
-    if (enqueue_step(e, false, e->n, e->n, 2)) return 1;            // ... density
+    // hash, sort, cell table, position reorder, row plans and the density sweep need positions only: they run while the
+    // velocities are still on their way in
+    if (enqueue_step(e, false, e->n, e->n, 1 | 2, true)) return 1;
     CK(cudaEventRecord(e->ev_copy[1], s));
     if (density_out) {                                              // rho leaves while the forces are computed
         CK(cudaStreamWaitEvent(c2, e->ev_copy[1], 0));
         unsort_scalar_kernel<<<g256, 256, 0, c2>>>(e->srho, e->sids, drho, e->n);
         CK(cudaMemcpyAsync(density_out, drho, n * sizeof(double), cudaMemcpyDeviceToHost, c2));
     }
-    if (enqueue_step(e, false, e->n, e->n, 4)) return 1;            // force + integrate + collide
+    CK(cudaStreamWaitEvent(s, e->ev_copy[0], 0));
+    pack_vec_kernel<double><<<g256, 256, 0, s>>>(dvel, e->vel_m, e->n);
+    if (enqueue_step(e, false, e->n, e->n, 4, true)) return 1;      // velocity gather, force + integrate + collide
     unpack_state_kernel<double><<<g256, 256, 0, s>>>(e->pos_m, e->vel_m, pos_out ? dpos : nullptr,
                                                      vel_out ? dvel : nullptr, (double *)nullptr, e->n);
     CK(cudaGetLastError());
@@ -654,7 +660,7 @@ int sph_compute_next_state(sph_handle_t e, const double *pos_in, const double *v
     CK(cudaStreamSynchronize(c2));
     e->has_state = true;
     e->steps_done += 1;
-    e->launches += e->launches_per_step + 4;
+    e->launches += e->launches_per_step + 5;   // + 2 packs, velocity gather, density unsort, unpack
     return 0;
 }
 

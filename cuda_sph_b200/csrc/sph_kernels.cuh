@@ -22,6 +22,7 @@ hash_kernel(const float4 *__restrict__ pos_m, uint32_t *__restrict__ keys, int n
 
 // ---- __populate_voxel_begins (voxel_sph_strategy.py:98-107) + gather into cell-contiguous SoA ---------------------
 // cell_range must be zeroed before the launch: an empty cell keeps (0, 0).
+template <bool WITH_VEL>
 __global__ void __launch_bounds__(256)
 reorder_kernel(const uint32_t *__restrict__ skeys, const uint32_t *__restrict__ sids,
                const float4 *__restrict__ pos_m, const float4 *__restrict__ vel_m, float4 *__restrict__ spos,
@@ -41,7 +42,20 @@ reorder_kernel(const uint32_t *__restrict__ skeys, const uint32_t *__restrict__ 
     }
     if (t == n - 1) cell_range[key].y = n;
     spos[t] = pos_m[id];
-    svel[t] = vel_m[id];
+    if (WITH_VEL) svel[t] = vel_m[id];
+}
+
+// Velocity half of the reorder, for callers whose velocities arrive late (sph_compute_next_state uploads them while the
+// density sweep runs): x, y, z only -- by then .w holds the pair factor the density sweep left there.
+__global__ void __launch_bounds__(256)
+gather_vel_kernel(const uint32_t *__restrict__ sids, const float4 *__restrict__ vel_m, float4 *__restrict__ svel, int n) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const float4 v = vel_m[sids[t]];
+    float *o = reinterpret_cast<float *>(svel + t);
+    o[0] = v.x;
+    o[1] = v.y;
+    o[2] = v.z;
 }
 
 // ---- x-slab mode only: make the order inside every cell ascending in GLOBAL particle id ------------------------------
