@@ -132,8 +132,7 @@ struct ForceAcc {
 // integrating_kernel + collision kernel in fp64 (base_kernels.py:30-98), scatter to the id-ordered master arrays.
 template <bool RECORD_TERMS>
 __device__ __forceinline__ void finish_particle(const SweepArgs &a, const StepConsts &c, int t, const float4 pi,
-                                                const float4 vi, float rho_i, ForceAcc f) {
-    const uint32_t id = a.sids[t];
+                                                const float4 vi, float rho_i, ForceAcc f, uint32_t id) {
     if ((int)id >= a.n_own) return;              // ghost particle of an x-slab: its owner integrates it
     if (a.gid && a.gid[id] < 0) return;          // empty slot of an x-slab (hole left by an emigrant / unused capacity)
     if (f.any) {  // with no neighbour besides self the reference's sums stay exactly 0 (and rho_i is 0)
@@ -460,7 +459,7 @@ force_kernel(const SweepArgs a, const GridDesc g, const StepConsts c) {
     const bool live = key != (uint32_t)g.ncells;
     const int2 cr = live ? __ldg(&a.cell_range[key]) : make_int2(0, 0);
     if (valid && !live)   // dead particle: F = external force, rho = 0 (reference NaN semantics carry on)
-        finish_particle<RECORD>(a, c, t, a.spos[t], a.svel[t], a.srho[t], ForceAcc());
+        finish_particle<RECORD>(a, c, t, a.spos[t], a.svel[t], a.srho[t], ForceAcc(), a.sids[t]);
     unsigned leaders = __ballot_sync(FULL, live && (((t - cr.x) & 31) == 0));
 
     while (leaders) {
@@ -554,7 +553,7 @@ force_kernel(const SweepArgs a, const GridDesc g, const StepConsts c) {
                 f = ForceAcc();
                 thread_walk<true>(a, g, c, tt, pi, vi, a_i, dens, f);
             }
-            finish_particle<RECORD>(a, c, tt, pi, vi, rho_i, f);
+            finish_particle<RECORD>(a, c, tt, pi, vi, rho_i, f, a.sids[tt]);
         }
         __syncwarp();
     }

@@ -647,6 +647,7 @@ force_rows_kernel(const SweepArgs a, const GridDesc g, const StepConsts c) {
     // issued before the key arrives (their use depends on it, their address does not)
     const uint8_t cf_raw = (j < nb) ? a.ncnt[t] : (uint8_t)0;
     const float rho_raw = (j < nb) ? a.srho[t] : 0.f;
+    const uint32_t my_id = (j < nb) ? a.sids[t] : 0u;   // master slot of the epilogue's scatter
     __syncthreads();
     const bool any_live = __syncthreads_count(live) != 0;
 
@@ -741,7 +742,7 @@ force_rows_kernel(const SweepArgs a, const GridDesc g, const StepConsts c) {
             f = fw;
             fin = true;
         }
-        if (fin) finish_particle<RECORD>(a, c, t, pi, vi, rho_f, f);
+        if (fin) finish_particle<RECORD>(a, c, t, pi, vi, rho_f, f, my_id);
 
         if (pass >= RB_WARPS || (pass < 0 && tp_fits)) break;
         ++pass;
