@@ -323,14 +323,14 @@ __device__ __forceinline__ void rows_issue_planned(const SweepArgs &a, const Gri
 // segment tables while the rows are in flight.  ci: local cell index (density only).
 template <bool DENSITY>
 __device__ __forceinline__ void rows_setup_planned(const SweepArgs &a, const GridDesc &g, RowPlan &plan,
-                                                   DensityRowsSmem *ds, int nb, int t, uint32_t key, bool live,
-                                                   int &ci) {
+                                                   DensityRowsSmem *ds, int nb, int t, uint32_t key, uint32_t prev_key,
+                                                   bool live, int &ci) {
     const int j = threadIdx.x, lane = j & 31, warp = j >> 5;
     if (DENSITY) {
         // local cells of the tile and their 27 segments (as row slots)
         const bool mine = live && j < nb;
         bool first = false;
-        if (mine) first = (j == 0) || (a.skeys[t - 1] != key);
+        if (mine) first = (j == 0) || (prev_key != key);
         const unsigned bal = __ballot_sync(FULL, first);
         if (lane == 0) plan.wcount[warp] = __popc(bal);
         __syncthreads();   // also publishes row_lo / row_base
@@ -424,9 +424,12 @@ density_rows_kernel(const SweepArgs a, const GridDesc g, const StepConsts c) {
     const int p0 = blockIdx.x * RB_THREADS;
     const int t = p0 + j;
     const int nb = min(RB_THREADS, a.n - p0);
-    const uint32_t key = (j < nb) ? a.skeys[t] : (uint32_t)g.ncells;
-    const bool live = key != (uint32_t)g.ncells;
     if (warp == 0) rows_issue_planned<true>(a, g, plan, a.plans[blockIdx.x], sm.rows, nullptr);
+    // the prologue's loads, all issued up front (their use depends on the key, their addresses do not)
+    const uint32_t key = (j < nb) ? a.skeys[t] : (uint32_t)g.ncells;
+    const uint32_t prev_key = (j < nb && j > 0) ? a.skeys[t - 1] : 0xffffffffu;
+    const float4 pi_raw = (j < nb) ? a.spos[t] : make_float4(0.f, 0.f, 0.f, 0.f);
+    const bool live = key != (uint32_t)g.ncells;
     if (j < 8) sm.rows[RB_CAP + j] = make_float4(1e18f, 1e18f, 1e18f, 0.f);
     if (j < nb && !live) {   // dead particle: no neighbours
         a.srho[t] = 0.f;
@@ -440,7 +443,7 @@ density_rows_kernel(const SweepArgs a, const GridDesc g, const StepConsts c) {
     int cx = 0, cy = 0, cz = 0;
     bool want = false, walk = false;
     if (live) {
-        pi = a.spos[t];
+        pi = pi_raw;
         decode_cell(g, key, cx, cy, cz);
         want = !(cx < g.own_lo - 1 || cx > g.own_hi);   // x-slab: nobody needs the density of the outer ghost column
         walk = want && (!g.aligned || !own_cell_matches(g, pi, cx, cy, cz));
@@ -456,7 +459,7 @@ density_rows_kernel(const SweepArgs a, const GridDesc g, const StepConsts c) {
         bool ok;
         if (pass < 0) {   // whole tile: planned by rows_plan_kernel, or known not to fit
             ok = tp_fits;
-            if (ok) rows_setup_planned<true>(a, g, plan, &sm, nb, t, key, live, ci);
+            if (ok) rows_setup_planned<true>(a, g, plan, &sm, nb, t, key, prev_key, live, ci);
         } else {
             ok = rows_setup<true>(a, g, plan, sm.rows, nullptr, &sm, j0, j1, t, key, live, ci);
         }
@@ -689,7 +692,7 @@ force_rows_kernel(const SweepArgs a, const GridDesc g, const StepConsts c) {
             bool ok;
             if (pass < 0) {
                 ok = tp_fits;
-                if (ok) rows_setup_planned<false>(a, g, plan, nullptr, nb, t, key, live, ci);
+                if (ok) rows_setup_planned<false>(a, g, plan, nullptr, nb, t, key, 0u, live, ci);
             } else {
                 ok = rows_setup<false>(a, g, plan, sm.rpos, sm.rvel, nullptr, j0, j1, t, key, live, ci);
             }
