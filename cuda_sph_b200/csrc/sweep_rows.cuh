@@ -435,8 +435,12 @@ density_rows_kernel(const SweepArgs a, const GridDesc g, const StepConsts c) {
         a.srho[t] = 0.f;
         a.ncnt[t] = 0;
     }
-    __syncthreads();
-    if (__syncthreads_count(live) == 0) return;
+    __syncthreads();   // mbarrier initialised, row_lo / row_base of a planned tile published
+    {
+        const TilePlan &tp = a.plans[blockIdx.x];
+        const bool plan_fits = g.aligned && tp.fits != 0 && tp.slots > 0;   // implies live particles
+        if (!plan_fits && __syncthreads_count(live) == 0) return;
+    }
 
     // this thread's particle
     float4 pi = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -651,8 +655,10 @@ force_rows_kernel(const SweepArgs a, const GridDesc g, const StepConsts c) {
     const uint8_t cf_raw = (j < nb) ? a.ncnt[t] : (uint8_t)0;
     const float rho_raw = (j < nb) ? a.srho[t] : 0.f;
     const uint32_t my_id = (j < nb) ? a.sids[t] : 0u;   // master slot of the epilogue's scatter
-    __syncthreads();
-    const bool any_live = __syncthreads_count(live) != 0;
+    __syncthreads();   // mbarrier initialised, row_lo / row_base of a planned tile published
+    // a fitting plan implies live particles; otherwise count them (a tile of dead particles stages nothing)
+    const bool plan_fits = g.aligned && a.plans[blockIdx.x].fits != 0 && a.plans[blockIdx.x].slots > 0;
+    const bool any_live = plan_fits || __syncthreads_count(live) != 0;
 
     int cx = 0, cy = 0, cz = 0, my_cnt = 0;
     bool want = false, walk = false;
@@ -692,7 +698,7 @@ force_rows_kernel(const SweepArgs a, const GridDesc g, const StepConsts c) {
             bool ok;
             if (pass < 0) {
                 ok = tp_fits;
-                if (ok) rows_setup_planned<false>(a, g, plan, nullptr, nb, t, key, 0u, live, ci);
+                // planned tile: nothing left to set up (rows in flight since the first instruction of warp 0)
             } else {
                 ok = rows_setup<false>(a, g, plan, sm.rpos, sm.rvel, nullptr, j0, j1, t, key, live, ci);
             }
