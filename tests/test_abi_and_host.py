@@ -168,3 +168,24 @@ def test_start_states_are_seeded_and_in_domain():
     assert (s1.position >= 0).all() and (s1.position < params.space_size[0]).all()
     params, s3 = workloads.pipe_flow(1 << 15, seed=0)
     assert len(params.pipe.segments) == 6 and params.space_size[1] == params.space_size[2]
+
+
+def test_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the reference's CPU path = the oracle port, all host threads) needs no GPU and prints
+    ONE JSON line with the contract keys; under torchrun only rank 0 works."""
+    import json
+    import subprocess
+    import sys
+    cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--particles", "20000", "--steps", "2",
+           "--warmup", "1"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=dict(os.environ, RANK="0"))
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "particle-updates/sec" and d["higher_is_better"] is True
+    assert d["value"] > 0 and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    # any other rank exits 0 without output
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=dict(os.environ, RANK="1"))
+    assert out.returncode == 0 and not [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
