@@ -74,15 +74,24 @@ __device__ __noinline__ double r2_exact(float ax, float ay, float az, float bx, 
 
 // poly6 term (h^2 - r^2)^3.  Close to the cut-off h^2 - r^2 cancels: there it is formed from the fp64 r^2 (the reference
 // is fp64 throughout), which keeps the density of a particle whose only neighbours sit at the cut-off within tolerance.
+// The density of a particle is ONE of two sums over its list, chosen by its neighbour count alone (so that every code
+// path -- staged rows, 32-particle passes, one-thread walk, any slab decomposition -- produces the same bits):
+//   count > 8 : sum of poly6_fast (fp32; a term near the cut-off is negligible among >= 8 others)
+//   count <= 8: sum of poly6_term (terms near the cut-off from the fp64 r^2)
+// Both are written with explicit roundings: no FMA contraction may differ between call sites.
+__device__ __forceinline__ float poly6_fast(const StepConsts &c, float r2) {
+    const float d = __fsub_rn(c.h2, r2);
+    return __fmul_rn(__fmul_rn(d, d), d);
+}
 __device__ __forceinline__ float poly6_term(const StepConsts &c, float r2, float ax, float ay, float az, float bx,
                                             float by, float bz) {
     if (r2 > c.h2_near) {
         const double d = c.h2_d - r2_exact(ax, ay, az, bx, by, bz);
-        return (float)(d * d * d);
+        return (float)__dmul_rn(__dmul_rn(d, d), d);
     }
-    const float d = c.h2 - r2;
-    return d * d * d;
+    return poly6_fast(c, r2);
 }
+constexpr int kSparseCount = 8;   // neighbour counts up to this use the poly6_term sum
 
 __device__ __forceinline__ float pressure_coeff(const StepConsts &c, float rho) {
     return c.k * (rho - c.rho0) / (rho * rho);   // p / rho^2 with p = K (rho - RHO_0)
@@ -177,6 +186,7 @@ __device__ __noinline__ int thread_walk(const SweepArgs &a, const GridDesc &g, c
     int vx, vy, vz;
     if (!cell_of(g, pi.x, pi.y, pi.z, vx, vy, vz)) return 0;
     int cnt = 0;
+    float dens_fast = 0.f, dens_exact = 0.f;   // see poly6_fast / poly6_term: the count decides which one is the density
     for (int dx = -1; dx <= 1; ++dx) {
         const int x = vx + dx;
         if (x < 0 || x >= g.tx) continue;
@@ -202,15 +212,21 @@ __device__ __noinline__ int thread_walk(const SweepArgs &a, const GridDesc &g, c
                                 const float4 vj = __ldg(&a.svel[j]);
                                 f.pair(c, ddx, ddy, ddz, r2, a_i, pressure_coeff(c, rho_j), c.lap_c / rho_j, vi, vj);
                             } else {
-                                dens += poly6_term(c, r2, pi.x, pi.y, pi.z, pj.x, pj.y, pj.z);
+                                dens_fast = __fadd_rn(dens_fast, poly6_fast(c, r2));
+                                if (cnt < kSparseCount)
+                                    dens_exact = __fadd_rn(dens_exact, poly6_term(c, r2, pi.x, pi.y, pi.z, pj.x, pj.y, pj.z));
                             }
                         }
-                        if (++cnt >= kMaxNeighbours) return cnt;
+                        if (++cnt >= kMaxNeighbours) {
+                            dens = dens_fast;
+                            return cnt;
+                        }
                     }
                 }
             }
         }
     }
+    dens = (cnt <= kSparseCount) ? dens_exact : dens_fast;
     return cnt;
 }
 

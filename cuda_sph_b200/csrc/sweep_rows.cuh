@@ -397,7 +397,7 @@ __device__ __noinline__ float sparse_density(const StepConsts &c, const float4 *
         if (slot == self) continue;
         const float4 cj = rows[slot];
         const float dx = p.x - cj.x, dy = p.y - cj.y, dz = p.z - cj.z;
-        dens += poly6_term(c, fmaf(dz, dz, fmaf(dy, dy, dx * dx)), p.x, p.y, p.z, cj.x, cj.y, cj.z);
+        dens = __fadd_rn(dens, poly6_term(c, fmaf(dz, dz, fmaf(dy, dy, dx * dx)), p.x, p.y, p.z, cj.x, cj.y, cj.z));
     }
     return dens;
 }
@@ -547,9 +547,8 @@ density_rows_kernel(const SweepArgs a, const GridDesc g, const StepConsts c) {
                         const float dx = pj.x - cj[u].x, dy = pj.y - cj[u].y, dz = pj.z - cj[u].z;
                         const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
                         band = band || r2 > c.h2_lo;
-                        const float d = c.h2 - r2;
-                        const float w = (i + u < k && sl[u] != selfj) ? d * d * d : 0.f;
-                        dens += w;
+                        const float w = (i + u < k && sl[u] != selfj) ? poly6_fast(c, r2) : 0.f;
+                        dens = __fadd_rn(dens, w);
                     }
                 }
                 for (int i = k; i < kept; ++i) {   // spares beyond the 32nd: only matter if something gets rejected
@@ -568,15 +567,12 @@ density_rows_kernel(const SweepArgs a, const GridDesc g, const StepConsts c) {
                         const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
                         if (r2 > c.h2_lo && !in_range_exact(pj.x, pj.y, pj.z, cj.x, cj.y, cj.z, c.r2_max)) continue;
                         lrow[k++] = (uint16_t)slot;
-                        if (slot != selfj) {
-                            const float d = c.h2 - r2;
-                            dens += d * d * d;
-                        }
+                        if (slot != selfj) dens = __fadd_rn(dens, poly6_fast(c, r2));
                     }
                 }
                 // a sparse particle's density can hinge on one neighbour at the cut-off, where h^2 - r^2 cancels in fp32:
                 // redo the few terms with the fp64 r^2 (never taken by capped lists, where such a term is negligible)
-                if (k <= 8) dens = sparse_density(c, sm.rows, lrow, k, selfj, pj);
+                if (k <= kSparseCount) dens = sparse_density(c, sm.rows, lrow, k, selfj, pj);
                 uint8_t cflag = (uint8_t)k;
                 if (k < kMaxNeighbours && kept >= RB_KEEP) {
                     // the scan stopped on its budget and too many band candidates were rejected: redo exactly
