@@ -161,10 +161,12 @@ class SlabRunner:
         return out
 
     def _pack(self, idx: torch.Tensor, with_rng: bool) -> torch.Tensor:
-        parts = [self.P[idx].view(torch.uint8).reshape(len(idx), -1), self.V[idx].view(torch.uint8).reshape(len(idx), -1),
-                 self.G[idx].view(torch.uint8).reshape(len(idx), -1)]
+        k, pb = len(idx), self.P.element_size() * 4          # explicit widths: k may be 0
+        parts = [self.P[idx].contiguous().view(torch.uint8).reshape(k, pb),
+                 self.V[idx].contiguous().view(torch.uint8).reshape(k, pb),
+                 self.G[idx].contiguous().view(torch.uint8).reshape(k, 4)]
         if with_rng and self.R is not None:
-            parts.append(self.R[self.G[idx].long()].view(torch.uint8).reshape(len(idx), -1))
+            parts.append(self.R[self.G[idx].long()].contiguous().view(torch.uint8).reshape(k, 16))
         return torch.cat(parts, dim=1)
 
     def _unpack(self, rows: torch.Tensor, at: int, with_rng: bool) -> int:

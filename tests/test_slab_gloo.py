@@ -199,3 +199,49 @@ def test_balanced_bounds_puts_wider_slabs_at_the_ends():
     hist2[:8] = 131072
     b2 = balanced_bounds(hist2, 4)
     assert b2[0] == 0 and b2[-1] == 75 and np.diff(b2).min() >= HALO
+
+
+def test_slab_partition_properties():
+    """Random column histograms: both boundary planners give a monotone cover with every slab >= HALO wide, and the
+    native-exchange capacities stay symmetric."""
+    from hypothesis import given, settings
+    from hypothesis import strategies as hst
+    from cuda_sph_b200.slab import balanced_bounds, plan_capacities
+
+    @settings(max_examples=60, deadline=None)
+    @given(hst.integers(2, 8), hst.integers(0, 2 ** 31 - 1), hst.booleans())
+    def check(world, seed, pile):
+        rng = np.random.default_rng(seed)
+        ncol = int(rng.integers(world * HALO, 200))
+        hist = rng.integers(0, 5000, size=ncol)
+        if pile:
+            hist[ncol // 8:] = 0                     # everything in the first columns (dam-break)
+        for planner in (equal_count_bounds, balanced_bounds):
+            b = planner(hist, world)
+            assert len(b) == world + 1 and b[0] == 0 and b[-1] == ncol
+            assert all(y - x >= HALO for x, y in zip(b[:-1], b[1:]))
+        b = balanced_bounds(hist, world)
+        n = int(hist.sum())
+        plans = [plan_capacities(hist, b, r, n, False) for r in range(world)]
+        for a in range(world):
+            for c in range(world):
+                assert plans[a]["cap_m"][c] == plans[c]["cap_m"][a] and plans[a]["cap_g"][c] == plans[c]["cap_g"][a]
+            assert plans[a]["own_cap"] >= int(hist[b[a]:b[a + 1]].sum())
+
+    check()
+
+
+def test_single_exchange_runner_without_a_process_group():
+    """world == 1: the single-exchange runner degenerates to the plain step (no halo, no migration)."""
+    orc.set_exact_pow(False)
+    n, params, st, P = _case("BOX")
+    n_cols = int(np.ceil(params.space_size[0] / params.voxel_size[0]))
+    run = OracleSingleExchangeRunner(P, n, capacity=2 * n, n_cols=n_cols, bounds=[0, n_cols], pipe_mode=False)
+    run.load_global(st.position, st.velocity)
+    run.step(2)
+    pos, vel, rho = run.gather_global(n)
+    p, v = st.position, st.velocity
+    for _ in range(2):
+        r = orc.step(P, p, v, light=True)
+        p, v = r.position, r.velocity
+    assert same(pos, p) and same(vel, v) and same(rho, r.density)
