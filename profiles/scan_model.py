@@ -74,7 +74,8 @@ rng = np.random.default_rng(0)
 tiles = rng.choice(n // 128, size=min(400, n // 128), replace=False)
 res = {"sorted order (current)": 0, "tile sorted by scan length": 0, "per-cell fast/slow halves": 0,
        "flat iterator, sorted order": 0, "flat iterator, tile sorted by scan length": 0,
-       "flat iterator, 2 particles per lane (long + short)": 0, "ideal (mean)": 0}
+       "flat iterator, 2 particles per lane (long + short)": 0, "flat iterator, tile sorted by fractional x": 0,
+       "flat iterator, 2 per lane paired by fractional x": 0, "ideal (mean)": 0}
 for tb in tiles:
     t0 = tb * 128
     idx = np.arange(t0, t0 + 128)
@@ -93,6 +94,11 @@ for tb in tiles:
     res["flat iterator, tile sorted by scan length"] += sum(scan[by_len[w * 32:(w + 1) * 32]].max() for w in range(4))
     pair = scan[by_len][:64] + scan[by_len][::-1][:64]      # shortest with longest on one lane, two warps of 32 lanes
     res["flat iterator, 2 particles per lane (long + short)"] += pair[:32].max() + pair[32:].max()
+    fx = sp[idx, 0] / vox - np.floor(sp[idx, 0] / vox)       # the cheap predictor: dx is the outermost walk dimension
+    by_fx = idx[np.argsort(fx, kind="stable")]
+    res["flat iterator, tile sorted by fractional x"] += sum(scan[by_fx[w * 32:(w + 1) * 32]].max() for w in range(4))
+    pair = scan[by_fx][:64] + scan[by_fx][::-1][:64]
+    res["flat iterator, 2 per lane paired by fractional x"] += pair[:32].max() + pair[32:].max()
     halves = np.asarray(fast + slow)
     res["per-cell fast/slow halves"] += sum(warp_steps(halves[w * 32:(w + 1) * 32]) for w in range(4))
 print(f"dam-break, N={n}: scan length mean {scan.mean():.0f}, median {np.median(scan):.0f}, p90 "
