@@ -20,8 +20,10 @@ device-to-device copy outside the timed events).  `--window 0` disables that and
 
 `value`  : N x steps / device time, inputs resident in HBM, L2 flushed between steps (per-step CUDA events summed).
 `e2e`    : the same through the reference-facing call compute_next_state (fp64 host buffers in pinned memory,
-           H2D + step + D2H every step), wall clock around the synchronous calls.
-`roofline`: dominant kernel (force sweep), algorithmic bytes / CUDA-event duration vs MEASURED_PEAKS.json.
+           H2D + step + D2H every step; copies interleaved with the step on two streams), wall clock around the
+           synchronous calls.
+`roofline`: dominant kernel (the density sweep), algorithmic bytes / CUDA-event duration vs MEASURED_PEAKS.json, its
+           measured DRAM traffic (ncu, profiles/traffic.json) and the issue-slot roofline that actually binds it.
 `cpu_baseline`: the oracle port timed on this box's host cores on a bounded sample of the same workload.
 """
 from __future__ import annotations
