@@ -10,7 +10,6 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsph_b200.so")
 SOURCES = ["sph_engine.cu"]
-HEADERS = ["sph_common.cuh", "radix_sort.cuh", "collide.cuh", "sph_kernels.cuh", "sweep.cuh", "sweep_rows.cuh", "../../include/sph_b200.h"]
 
 
 def nvcc_path() -> str:
@@ -24,7 +23,9 @@ def needs_build() -> bool:
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [os.path.abspath(__file__)]
+    # every header of csrc/ (all are reachable from sph_engine.cu) + the public header + this script
+    deps = [os.path.join(CSRC, s) for s in os.listdir(CSRC) if s.endswith((".cu", ".cuh", ".h"))]
+    deps += [os.path.join(HERE, "..", "include", "sph_b200.h"), os.path.abspath(__file__)]
     return any(os.path.getmtime(d) > t for d in deps)
 
 

@@ -29,6 +29,7 @@ struct StepConsts {
     float h;
     float h2_lo, h2_hi;  // band around h^2 inside which the fp64 predicate decides
     float h2;
+    float h2_sup;        // h^2 (1 + band) of density_flat_kernel's superset test (band covers its expanded-form rounding)
     float h2_near;       // above this r^2 the poly6 term (h^2 - r^2)^3 is evaluated from an fp64 r^2 (cancellation)
     float w_mass;        // W_CONST * MASS                       (config.py:27, voxel_kernels.py:132)
     float grad_c;        // GRAD_W_CONST                         (config.py:28)

@@ -18,6 +18,7 @@
 #include "slab_exchange.cuh"
 #include "sph_kernels.cuh"
 #include "sweep.cuh"
+#include "sweep_flat.cuh"
 #include "sweep_rows.cuh"
 
 using namespace sph;
@@ -58,6 +59,8 @@ struct SphEngine {
     uint32_t *skeys = nullptr, *sids = nullptr;  // aliases of the final sort buffers
     uint32_t *block_hist = nullptr, *digit_total = nullptr;
     TilePlan *tile_plans = nullptr;   // one row plan per 128-particle tile of the sweeps (rows_plan_kernel)
+    int *refused = nullptr;           // [0] = count, [1..] = tiles density_flat_kernel left to the row-staged fallback
+    bool flat_density = true;         // SPH_DENSITY=rows: every tile through density_rows_kernel
     uint32_t *os_ctrl = nullptr;      // onesweep control block (histograms, tickets, look-back status)
     bool onesweep = true;         // SPH_SORT=classic selects the three-kernel passes of radix_sort.cuh
     bool sort_lookback = false;   // SPH_SORT=lookback: decoupled look-back passes (one kernel per digit) instead of count + scan
@@ -204,6 +207,7 @@ int sph_create(const SphParams *params, int device, sph_handle_t *out) {
         e->grid.inv_voxel[d] = (float)(1.0 / params->voxel_size[d]);
     }
     if (const char *sw = getenv("SPH_SWEEP")) e->rows_sweeps = strcmp(sw, "warp") != 0;
+    if (const char *sd = getenv("SPH_DENSITY")) e->flat_density = strcmp(sd, "rows") != 0;
     e->slab = (params->flags & SPH_FLAG_SLAB) != 0;
     long long table_cells = ncells;
     if (e->slab) {
@@ -229,6 +233,12 @@ int sph_create(const SphParams *params, int device, sph_handle_t *out) {
     c.h2_d = h * h;
     c.h2_lo = (float)(h * h * (1.0 - 1e-5));
     c.h2_hi = (float)(h * h * (1.0 + 1e-5));
+    {   // superset band of density_flat_kernel: 16 x 2^-24 x (sum of the magnitudes its expanded r^2 adds up), >= 2e-5
+        const double *v = params->voxel_size;
+        const double mag = 25.0 * (v[1] * v[1] + v[2] * v[2]) + 4.0 * v[0] * v[0] + h * h;
+        const double band = std::max(2e-5, 16.0 * std::ldexp(1.0, -24) * mag / (h * h));
+        c.h2_sup = (float)(h * h * (1.0 + band));
+    }
     c.w_mass = (float)(315.0 / (64.0 * M_PI * std::pow(h, 9.0)) * params->mass);
     c.grad_c = (float)(-45.0 / (M_PI * std::pow(h, 6.0)));
     c.lap_c = (float)(45.0 / (M_PI * std::pow(h, 6.0)));
@@ -286,6 +296,7 @@ int sph_create(const SphParams *params, int device, sph_handle_t *out) {
     if (e->passes > OS_MAX_PASSES) e->onesweep = false;
     ALLOC(e->os_ctrl, os_ctrl_words(e->passes, (n + OS_TILE - 1) / OS_TILE));
     ALLOC(e->tile_plans, (n + RB_THREADS - 1) / RB_THREADS);
+    ALLOC(e->refused, (n + RB_THREADS - 1) / RB_THREADS + 1);
     ALLOC(e->cell_range, e->cell_capacity);
     if (e->slab) ALLOC(e->gid, n);
     ALLOC(e->stats_d, 4);
@@ -324,12 +335,15 @@ int sph_create(const SphParams *params, int device, sph_handle_t *out) {
     e->own_stream = true;
     for (auto &ev : e->ev) cudaEventCreate(&ev);
     cudaFuncSetAttribute(density_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DensityRowsSmem));
+    cudaFuncSetAttribute(density_rows_fallback_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)sizeof(DensityRowsSmem));
+    cudaFuncSetAttribute(density_flat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FlatSmem));
     cudaFuncSetAttribute(force_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)sizeof(ForceRowsSmem));
     cudaFuncSetAttribute(force_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)sizeof(ForceRowsSmem));
     e->launches_per_step = 1 + (e->onesweep ? 2 + (e->sort_lookback ? 1 : 3) * e->passes : 3 * e->passes) + 1 + 1 + 1 + 1 +
-                           (e->rows_sweeps ? 1 : 0);
+                           (e->rows_sweeps ? (e->flat_density ? 2 : 1) : 0);
     if (cudaDeviceSynchronize() != cudaSuccess) {
         sph_destroy(e);
         return fail("device error during create");
@@ -344,7 +358,7 @@ int sph_destroy(sph_handle_t e) {
     cudaDeviceSynchronize();
     invalidate_graph(e);
     void *ptrs[] = {e->pos_m, e->vel_m, e->spos, e->svel, e->sforce, e->spress, e->svisc, e->srho, e->nlist, e->ncnt,
-                    e->keys, e->ka, e->va, e->kb, e->vb, e->block_hist, e->digit_total, e->os_ctrl, e->tile_plans, e->cell_range, e->pipe_d,
+                    e->keys, e->ka, e->va, e->kb, e->vb, e->block_hist, e->digit_total, e->os_ctrl, e->tile_plans, e->refused, e->cell_range, e->pipe_d,
                     e->rng, e->gid, e->stage, e->stats_d, e->snap_pos, e->snap_vel, e->snap_rng, e->sendbuf, e->recvbuf,
                     e->slab_counters, e->tmp_gid};
     for (void *q : ptrs)
@@ -526,8 +540,16 @@ static int enqueue_step(SphEngine *e, bool timed, int n, int n_own, int stages =
     if (e->rows_sweeps) {
         const int grb = (n + RB_THREADS - 1) / RB_THREADS;
         if (stages & 2) {
-            rows_plan_kernel<<<(grb + RP_WARPS - 1) / RP_WARPS, RP_WARPS * 32, 0, s>>>(sa, e->grid, e->tile_plans, grb);
-            density_rows_kernel<<<grb, RB_THREADS, sizeof(DensityRowsSmem), s>>>(sa, e->grid, e->consts);
+            rows_plan_kernel<<<(grb + RP_WARPS - 1) / RP_WARPS, RP_WARPS * 32, 0, s>>>(sa, e->grid, e->tile_plans, grb,
+                                                                                       e->refused);
+            if (e->flat_density) {
+                const FlatArgs fa{e->refused + 1, e->refused};
+                density_flat_kernel<<<grb, FL_THREADS, sizeof(FlatSmem), s>>>(sa, e->grid, e->consts, fa);
+                density_rows_fallback_kernel<<<std::min(grb, 148 * 2), RB_THREADS, sizeof(DensityRowsSmem), s>>>(
+                    sa, e->grid, e->consts, e->refused + 1, e->refused);
+            } else {
+                density_rows_kernel<<<grb, RB_THREADS, sizeof(DensityRowsSmem), s>>>(sa, e->grid, e->consts);
+            }
         }
         if (timed) cudaEventRecord(e->ev[4], s);
         if (!(stages & 4)) {

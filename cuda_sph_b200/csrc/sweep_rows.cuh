@@ -61,6 +61,9 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+__device__ __forceinline__ void mbar_inval(void *bar) {
+    asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait(void *bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
@@ -227,8 +230,10 @@ struct TilePlan {
 constexpr int RP_WARPS = 8;
 
 __global__ void __launch_bounds__(RP_WARPS * 32)
-rows_plan_kernel(const SweepArgs a, const GridDesc g, TilePlan *__restrict__ plans, int ntiles) {
+rows_plan_kernel(const SweepArgs a, const GridDesc g, TilePlan *__restrict__ plans, int ntiles,
+                 int *__restrict__ n_refused) {
     const int lane = threadIdx.x & 31;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *n_refused = 0;   // tile list of density_rows_fallback_kernel
     const int tile = blockIdx.x * RP_WARPS + (threadIdx.x >> 5);
     if (tile >= ntiles) return;
     const int p0 = tile * RB_THREADS;
@@ -415,16 +420,15 @@ __device__ __forceinline__ void publish_density(const SweepArgs &a, const StepCo
     const_cast<float *>(reinterpret_cast<const float *>(a.svel + t))[3] = c.lap_c / rho;
 }
 
-__global__ void __launch_bounds__(RB_THREADS, RB_DENSITY_CTAS)
-density_rows_kernel(const SweepArgs a, const GridDesc g, const StepConsts c) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    DensityRowsSmem &sm = *reinterpret_cast<DensityRowsSmem *>(smem_raw);
+// One tile (128 consecutive sorted particles) of the row-staged density sweep; CTA-uniform control flow.
+__device__ __forceinline__ void density_rows_tile(const SweepArgs &a, const GridDesc &g, const StepConsts &c,
+                                                  const int tile, DensityRowsSmem &sm) {
     RowPlan &plan = sm.plan;
     const int j = threadIdx.x, lane = j & 31, warp = j >> 5;
-    const int p0 = blockIdx.x * RB_THREADS;
+    const int p0 = tile * RB_THREADS;
     const int t = p0 + j;
     const int nb = min(RB_THREADS, a.n - p0);
-    if (warp == 0) rows_issue_planned<true>(a, g, plan, a.plans[blockIdx.x], sm.rows, nullptr);
+    if (warp == 0) rows_issue_planned<true>(a, g, plan, a.plans[tile], sm.rows, nullptr);
     // the prologue's loads, all issued up front (their use depends on the key, their addresses do not)
     const uint32_t key = (j < nb) ? a.skeys[t] : (uint32_t)g.ncells;
     const uint32_t prev_key = (j < nb && j > 0) ? a.skeys[t - 1] : 0xffffffffu;
@@ -437,7 +441,7 @@ density_rows_kernel(const SweepArgs a, const GridDesc g, const StepConsts c) {
     }
     __syncthreads();   // mbarrier initialised, row_lo / row_base of a planned tile published
     {
-        const TilePlan &tp = a.plans[blockIdx.x];
+        const TilePlan &tp = a.plans[tile];
         const bool plan_fits = g.aligned && tp.fits != 0 && tp.slots > 0;   // implies live particles
         if (!plan_fits && __syncthreads_count(live) == 0) return;
     }
@@ -454,7 +458,7 @@ density_rows_kernel(const SweepArgs a, const GridDesc g, const StepConsts c) {
     }
 
     uint32_t parity = 0;
-    const bool tp_fits = g.aligned && a.plans[blockIdx.x].fits != 0;
+    const bool tp_fits = g.aligned && a.plans[tile].fits != 0;
     // -1: whole CTA; 0..RB_WARPS-1: one warp's particles; RB_WARPS: no staging at all (everyone walks)
     int pass = g.aligned ? -1 : RB_WARPS;
     int j0 = 0, j1 = nb;
@@ -627,6 +631,29 @@ density_rows_kernel(const SweepArgs a, const GridDesc g, const StepConsts c) {
             const int wc = thread_walk<false>(a, g, c, t, pi, pi, 0.f, dens, dummy);
             publish_density(a, c, t, dens, (uint8_t)wc | CNT_WALK);
         }
+    }
+}
+
+// Whole grid through the row-staged sweep (SPH_DENSITY=rows: A/B against density_flat_kernel of sweep_flat.cuh).
+__global__ void __launch_bounds__(RB_THREADS, RB_DENSITY_CTAS)
+density_rows_kernel(const SweepArgs a, const GridDesc g, const StepConsts c) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    density_rows_tile(a, g, c, blockIdx.x, *reinterpret_cast<DensityRowsSmem *>(smem_raw));
+}
+
+// The tiles density_flat_kernel left (Q2 grids, tiles whose rows / column blocks exceed its shared memory): a small
+// persistent grid runs down the list.
+__global__ void __launch_bounds__(RB_THREADS, RB_DENSITY_CTAS)
+density_rows_fallback_kernel(const SweepArgs a, const GridDesc g, const StepConsts c, const int *__restrict__ refused,
+                             const int *__restrict__ n_refused) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    DensityRowsSmem &sm = *reinterpret_cast<DensityRowsSmem *>(smem_raw);
+    const int n = *n_refused;
+    for (int i = blockIdx.x; i < n; i += gridDim.x) {
+        density_rows_tile(a, g, c, refused[i], sm);
+        __syncthreads();
+        if (threadIdx.x == 0) mbar_inval(&sm.plan.mbar);   // the next tile initialises it again
+        __syncthreads();
     }
 }
 
