@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsph_b200.so")
+# SPH_B200_LIB: developer knob for A/B runs of variant builds (build.build_variant); the product library otherwise
+LIB_PATH = os.environ.get("SPH_B200_LIB") or os.path.join(_HERE, "libsph_b200.so")
 
 MODE_BOX, MODE_PIPE = 0, 1
 FLAG_RECORD_NEIGHBOUR_COUNTS, FLAG_RECORD_TERMS, FLAG_NO_GRAPH, FLAG_SLAB = 1, 2, 4, 8

@@ -29,12 +29,19 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build_variant(name: str, defines: list[str]) -> str:
+    """A/B build with extra -D flags (tile sizes, staging capacities ...) next to the product library."""
+    return build(force=True, out=os.path.join(HERE, f"libsph_b200_{name}.so"), defines=defines)
+
+
+def build(force: bool = False, verbose: bool = False, out: str | None = None, defines: list[str] | None = None) -> str:
     if not force and not needs_build():
         return LIB
+    LIB_OUT = out or LIB
     cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
            "--shared", "-Xcompiler", "-fPIC", "-ccbin", "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++",
-           "-I", os.path.join(HERE, "..", "include"), "-o", LIB]
+           "-I", os.path.join(HERE, "..", "include"), "-o", LIB_OUT]
+    cmd += [f"-D{d}" for d in (defines or [])]
     if verbose:
         cmd += ["-Xptxas", "-v"]
     cmd += [os.path.join(CSRC, s) for s in SOURCES]
@@ -43,7 +50,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
     if verbose:
         print(res.stderr)
-    return LIB
+    return LIB_OUT
 
 
 if __name__ == "__main__":

@@ -59,7 +59,7 @@ struct SphEngine {
     uint32_t *skeys = nullptr, *sids = nullptr;  // aliases of the final sort buffers
     uint32_t *block_hist = nullptr, *digit_total = nullptr;
     TilePlan *tile_plans = nullptr;   // one row plan per 128-particle tile of the sweeps (rows_plan_kernel)
-    int *refused = nullptr;           // [0] = count, [1..] = tiles density_flat_kernel left to the row-staged fallback
+    int *refused = nullptr;           // [0] = count, [1..] = work items density_flat_kernel left to the row-staged fallback
     bool flat_density = true;         // SPH_DENSITY=rows: every tile through density_rows_kernel
     uint32_t *os_ctrl = nullptr;      // onesweep control block (histograms, tickets, look-back status)
     bool onesweep = true;         // SPH_SORT=classic selects the three-kernel passes of radix_sort.cuh
@@ -296,7 +296,7 @@ int sph_create(const SphParams *params, int device, sph_handle_t *out) {
     if (e->passes > OS_MAX_PASSES) e->onesweep = false;
     ALLOC(e->os_ctrl, os_ctrl_words(e->passes, (n + OS_TILE - 1) / OS_TILE));
     ALLOC(e->tile_plans, (n + RB_THREADS - 1) / RB_THREADS);
-    ALLOC(e->refused, (n + RB_THREADS - 1) / RB_THREADS + 1);
+    ALLOC(e->refused, 4 * (size_t)((n + RB_THREADS - 1) / RB_THREADS) + 1);
     ALLOC(e->cell_range, e->cell_capacity);
     if (e->slab) ALLOC(e->gid, n);
     ALLOC(e->stats_d, 4);
@@ -545,7 +545,7 @@ static int enqueue_step(SphEngine *e, bool timed, int n, int n_own, int stages =
             if (e->flat_density) {
                 const FlatArgs fa{e->refused + 1, e->refused};
                 density_flat_kernel<<<grb, FL_THREADS, sizeof(FlatSmem), s>>>(sa, e->grid, e->consts, fa);
-                density_rows_fallback_kernel<<<std::min(grb, 148 * 2), RB_THREADS, sizeof(DensityRowsSmem), s>>>(
+                density_rows_fallback_kernel<<<std::min(4 * grb, 148 * 4), RB_THREADS, sizeof(DensityRowsSmem), s>>>(
                     sa, e->grid, e->consts, e->refused + 1, e->refused);
             } else {
                 density_rows_kernel<<<grb, RB_THREADS, sizeof(DensityRowsSmem), s>>>(sa, e->grid, e->consts);

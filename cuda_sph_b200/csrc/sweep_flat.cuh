@@ -32,13 +32,18 @@
 namespace sph {
 
 constexpr int FL_THREADS = RB_THREADS;   // one tile of the force sweep (its TilePlan defines the list slots)
-constexpr int FL_CAP = 2560;             // staged candidates per tile
+#ifndef SPH_FL_CAP
+#define SPH_FL_CAP 2560
+#define SPH_FL_MAXR 24
+#define SPH_FL_CTAS 4
+#endif
+constexpr int FL_CAP = SPH_FL_CAP;       // staged candidates per tile
 constexpr int FL_SLACK = 32;             // the scan reads up to one round past a window
 constexpr int FL_MAXC = RB_MAXC;         // non-empty cells per tile
 constexpr int FL_MAXB = 80;              // column blocks per tile
-constexpr int FL_MAXR = 24;              // 32-candidate rounds per particle (longer windows: one-thread walk)
+constexpr int FL_MAXR = SPH_FL_MAXR;              // 32-candidate rounds per particle (longer windows: one-thread walk)
 constexpr int FL_KEEP = 34;              // superset hits after which a lane stops scanning (32 + spares for rejections)
-constexpr int FL_CTAS = 4;
+constexpr int FL_CTAS = SPH_FL_CTAS;
 static_assert(FL_THREADS == 128, "density_flat_kernel is written for 128-particle tiles");
 
 struct FlatSmem {
@@ -64,12 +69,12 @@ struct FlatSmem {
     int row_lo[9], row_base[10];
     int wsum[FL_THREADS / 32], wsum2[FL_THREADS / 32], wcount[FL_THREADS / 32];
 };
-static_assert(sizeof(FlatSmem) <= 56 * 1024, "four CTAs per SM");
+static_assert(sizeof(FlatSmem) <= (228 / FL_CTAS - 1) * 1024, "FL_CTAS CTAs per SM");
 // finished lanes keep stepping with their warp: everything they may read lies inside the arrays
 static_assert((3 * (FL_CAP + FL_SLACK) + FL_MAXR * 32) * 4 <= (int)sizeof(FlatSmem), "scan overrun must stay inside FlatSmem");
 
 struct FlatArgs {
-    int *refused;      // tiles left to density_rows_fallback_kernel
+    int *refused;      // work left to density_rows_fallback_kernel: tile * 8 + (0: whole tile | 1 + pass)
     int *n_refused;    // zeroed by rows_plan_kernel
 };
 
@@ -161,7 +166,21 @@ density_flat_kernel(const SweepArgs a, const GridDesc g, const StepConsts c, con
     }
     if (ncell == 0) return;   // nothing alive in this tile
     const int ci = coff + __popc(bal & lanemask_le_()) - 1;
-    bool refuse = !g.aligned || !tp_fits || ncell > FL_MAXC;   // CTA-uniform
+    bool refuse = false;   // CTA-uniform
+    auto hand_over = [&]() {   // rows that fit the force sweep's staging: one item; else its four 32-particle passes
+        if (j == 0) {
+            if (!g.aligned || tp_fits) {
+                fa.refused[atomicAdd(fa.n_refused, 1)] = tile * 8;
+            } else {
+                const int q = atomicAdd(fa.n_refused, 4);
+                for (int u = 0; u < 4; ++u) fa.refused[q + u] = tile * 8 + 1 + u;
+            }
+        }
+    };
+    if (!g.aligned || !tp_fits || ncell > FL_MAXC) {
+        hand_over();
+        return;
+    }
     int cx = 0, cy = 0, cz = 0;
     if (live) decode_cell(g, key, cx, cy, cz);
     if (!refuse && first) {
@@ -253,8 +272,8 @@ density_flat_kernel(const SweepArgs a, const GridDesc g, const StepConsts c, con
         staged += sm.wsum2[w];
     }
     refuse = refuse || staged > FL_CAP;
-    if (refuse) {   // CTA-uniform
-        if (j == 0) fa.refused[atomicAdd(fa.n_refused, 1)] = tile;
+    if (refuse) {
+        hand_over();
         return;
     }
     if (j < nblk) {

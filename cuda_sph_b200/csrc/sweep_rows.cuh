@@ -421,8 +421,10 @@ __device__ __forceinline__ void publish_density(const SweepArgs &a, const StepCo
 }
 
 // One tile (128 consecutive sorted particles) of the row-staged density sweep; CTA-uniform control flow.
+// only_pass >= 0: just that 32-particle pass (the fallback kernel spreads the passes of a tile whose rows do not fit
+// over four CTAs instead of running them one after the other with three warps idle).
 __device__ __forceinline__ void density_rows_tile(const SweepArgs &a, const GridDesc &g, const StepConsts &c,
-                                                  const int tile, DensityRowsSmem &sm) {
+                                                  const int tile, DensityRowsSmem &sm, const int only_pass = -1) {
     RowPlan &plan = sm.plan;
     const int j = threadIdx.x, lane = j & 31, warp = j >> 5;
     const int p0 = tile * RB_THREADS;
@@ -462,6 +464,12 @@ __device__ __forceinline__ void density_rows_tile(const SweepArgs &a, const Grid
     // -1: whole CTA; 0..RB_WARPS-1: one warp's particles; RB_WARPS: no staging at all (everyone walks)
     int pass = g.aligned ? -1 : RB_WARPS;
     int j0 = 0, j1 = nb;
+    if (only_pass >= 0 && g.aligned) {
+        pass = only_pass;
+        j0 = pass * 32;
+        j1 = min(nb, j0 + 32);
+        if (j0 >= nb) return;
+    }
     while (pass < RB_WARPS) {
         int ci = 0;
         bool ok;
@@ -617,7 +625,7 @@ __device__ __forceinline__ void density_rows_tile(const SweepArgs &a, const Grid
                 publish_density(a, c, t, dens, (uint8_t)wc | CNT_WALK);
             }
         }
-        if (ok && pass < 0) break;
+        if ((ok && pass < 0) || only_pass >= 0) break;
         ++pass;
         if (pass * 32 >= nb) break;
         j0 = pass * 32;
@@ -650,7 +658,8 @@ density_rows_fallback_kernel(const SweepArgs a, const GridDesc g, const StepCons
     DensityRowsSmem &sm = *reinterpret_cast<DensityRowsSmem *>(smem_raw);
     const int n = *n_refused;
     for (int i = blockIdx.x; i < n; i += gridDim.x) {
-        density_rows_tile(a, g, c, refused[i], sm);
+        const int item = refused[i];   // tile * 8 + (0: whole tile | 1 + pass)
+        density_rows_tile(a, g, c, item >> 3, sm, (item & 7) - 1);
         __syncthreads();
         if (threadIdx.x == 0) mbar_inval(&sm.plan.mbar);   // the next tile initialises it again
         __syncthreads();
