@@ -59,7 +59,12 @@ struct SphEngine {
     uint32_t *skeys = nullptr, *sids = nullptr;  // aliases of the final sort buffers
     uint32_t *block_hist = nullptr, *digit_total = nullptr;
     TilePlan *tile_plans = nullptr;   // one row plan per 128-particle tile of the sweeps (rows_plan_kernel)
-    int *refused = nullptr;           // [0] = count, [1..] = work items density_flat_kernel left to the row-staged fallback
+    // work items of the sweeps (tile * 8 + (0: whole tile | 1 + pass)): [0] = count of list A (passes of tiles whose rows
+    // do not fit; rows_plan_kernel), [1] = count of list B (whole tiles density_flat_kernel hands over), then the lists
+    int *refused = nullptr;
+    int ntiles_rb = 0;
+    cudaStream_t aux_stream = nullptr;   // the work-item kernels run here, next to the main sweeps
+    cudaEvent_t ev_fork[2]{}, ev_join[2]{};
     bool flat_density = true;         // SPH_DENSITY=rows: every tile through density_rows_kernel
     uint32_t *os_ctrl = nullptr;      // onesweep control block (histograms, tickets, look-back status)
     bool onesweep = true;         // SPH_SORT=classic selects the three-kernel passes of radix_sort.cuh
@@ -296,7 +301,8 @@ int sph_create(const SphParams *params, int device, sph_handle_t *out) {
     if (e->passes > OS_MAX_PASSES) e->onesweep = false;
     ALLOC(e->os_ctrl, os_ctrl_words(e->passes, (n + OS_TILE - 1) / OS_TILE));
     ALLOC(e->tile_plans, (n + RB_THREADS - 1) / RB_THREADS);
-    ALLOC(e->refused, 4 * (size_t)((n + RB_THREADS - 1) / RB_THREADS) + 1);
+    e->ntiles_rb = (n + RB_THREADS - 1) / RB_THREADS;
+    ALLOC(e->refused, 5 * (size_t)e->ntiles_rb + 2);
     ALLOC(e->cell_range, e->cell_capacity);
     if (e->slab) ALLOC(e->gid, n);
     ALLOC(e->stats_d, 4);
@@ -333,17 +339,33 @@ int sph_create(const SphParams *params, int device, sph_handle_t *out) {
         return fail("cudaStreamCreate failed");
     }
     e->own_stream = true;
+    {
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        if (cudaStreamCreateWithPriority(&e->aux_stream, cudaStreamNonBlocking, hi) != cudaSuccess) {
+            sph_destroy(e);
+            return fail("cudaStreamCreate failed");
+        }
+        for (int i = 0; i < 2; ++i) {
+            cudaEventCreateWithFlags(&e->ev_fork[i], cudaEventDisableTiming);
+            cudaEventCreateWithFlags(&e->ev_join[i], cudaEventDisableTiming);
+        }
+    }
     for (auto &ev : e->ev) cudaEventCreate(&ev);
     cudaFuncSetAttribute(density_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DensityRowsSmem));
-    cudaFuncSetAttribute(density_rows_fallback_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)sizeof(DensityRowsSmem));
     cudaFuncSetAttribute(density_flat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FlatSmem));
+    cudaFuncSetAttribute(density_rows_items_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)sizeof(DensityRowsSmem));
+    cudaFuncSetAttribute(force_rows_items_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)sizeof(ForceRowsSmem));
+    cudaFuncSetAttribute(force_rows_items_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)sizeof(ForceRowsSmem));
     cudaFuncSetAttribute(force_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)sizeof(ForceRowsSmem));
     cudaFuncSetAttribute(force_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)sizeof(ForceRowsSmem));
     e->launches_per_step = 1 + (e->onesweep ? 2 + (e->sort_lookback ? 1 : 3) * e->passes : 3 * e->passes) + 1 + 1 + 1 + 1 +
-                           (e->rows_sweeps ? (e->flat_density ? 2 : 1) : 0);
+                           (e->rows_sweeps ? (e->flat_density ? 4 : 3) : 0);
     if (cudaDeviceSynchronize() != cudaSuccess) {
         sph_destroy(e);
         return fail("device error during create");
@@ -367,6 +389,11 @@ int sph_destroy(sph_handle_t e) {
         if (ev) cudaEventDestroy(ev);
     if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
+    if (e->aux_stream) cudaStreamDestroy(e->aux_stream);
+    for (int i = 0; i < 2; ++i) {
+        if (e->ev_fork[i]) cudaEventDestroy(e->ev_fork[i]);
+        if (e->ev_join[i]) cudaEventDestroy(e->ev_join[i]);
+    }
     for (auto &ev : e->ev_copy)
         if (ev) cudaEventDestroy(ev);
     delete e;
@@ -511,9 +538,11 @@ static int enqueue_step(SphEngine *e, bool timed, int n, int n_own, int stages =
                                                   (uint32_t)e->grid.ncells);
         }
         if (split_vel)
-            reorder_kernel<false><<<g256, 256, 0, s>>>(e->skeys, sids, e->pos_m, e->vel_m, e->spos, e->svel, e->cell_range, n);
+            reorder_kernel<false><<<g256, 256, 0, s>>>(e->skeys, sids, e->pos_m, e->vel_m, e->spos, e->svel, e->cell_range, n,
+                                                       e->refused);
         else
-            reorder_kernel<true><<<g256, 256, 0, s>>>(e->skeys, sids, e->pos_m, e->vel_m, e->spos, e->svel, e->cell_range, n);
+            reorder_kernel<true><<<g256, 256, 0, s>>>(e->skeys, sids, e->pos_m, e->vel_m, e->spos, e->svel, e->cell_range, n,
+                                                      e->refused);
     }
     if ((stages & 4) && split_vel) gather_vel_kernel<<<g256, 256, 0, s>>>(sids, e->vel_m, e->svel, n);
     if (timed) cudaEventRecord(e->ev[3], s);
@@ -537,26 +566,46 @@ static int enqueue_step(SphEngine *e, bool timed, int n, int n_own, int stages =
     sa.n = n;
     sa.n_own = n_own;
     sa.plans = e->tile_plans;
+    sa.n_items = e->refused;
+    sa.items = e->refused + 2;
     if (e->rows_sweeps) {
         const int grb = (n + RB_THREADS - 1) / RB_THREADS;
+        cudaStream_t x = e->aux_stream;
+        int *list_b = e->refused + 2 + 4 * (size_t)e->ntiles_rb;
         if (stages & 2) {
             rows_plan_kernel<<<(grb + RP_WARPS - 1) / RP_WARPS, RP_WARPS * 32, 0, s>>>(sa, e->grid, e->tile_plans, grb,
-                                                                                       e->refused);
+                                                                                       e->refused, e->refused + 2);
+            // fork: the passes of tiles whose rows do not fit run next to the main density sweep
+            cudaEventRecord(e->ev_fork[0], s);
+            cudaStreamWaitEvent(x, e->ev_fork[0], 0);
+            density_rows_items_kernel<<<ITEM_CTAS, RB_THREADS, sizeof(DensityRowsSmem), x>>>(sa, e->grid, e->consts,
+                                                                                             sa.n_items, sa.items);
+            cudaEventRecord(e->ev_join[0], x);
             if (e->flat_density) {
-                const FlatArgs fa{e->refused + 1, e->refused};
+                const FlatArgs fa{list_b, e->refused + 1};
                 density_flat_kernel<<<grb, FL_THREADS, sizeof(FlatSmem), s>>>(sa, e->grid, e->consts, fa);
-                density_rows_fallback_kernel<<<std::min(4 * grb, 148 * 4), RB_THREADS, sizeof(DensityRowsSmem), s>>>(
-                    sa, e->grid, e->consts, e->refused + 1, e->refused);
+                density_rows_items_kernel<<<ITEM_CTAS, RB_THREADS, sizeof(DensityRowsSmem), s>>>(
+                    sa, e->grid, e->consts, e->refused + 1, list_b);
             } else {
                 density_rows_kernel<<<grb, RB_THREADS, sizeof(DensityRowsSmem), s>>>(sa, e->grid, e->consts);
             }
+            cudaStreamWaitEvent(s, e->ev_join[0], 0);
         }
         if (timed) cudaEventRecord(e->ev[4], s);
-        if (!(stages & 4)) {
-        } else if (e->spress)
-            force_rows_kernel<true><<<grb, RB_THREADS, sizeof(ForceRowsSmem), s>>>(sa, e->grid, e->consts);
-        else
-            force_rows_kernel<false><<<grb, RB_THREADS, sizeof(ForceRowsSmem), s>>>(sa, e->grid, e->consts);
+        if (stages & 4) {
+            cudaEventRecord(e->ev_fork[1], s);
+            cudaStreamWaitEvent(x, e->ev_fork[1], 0);
+            if (e->spress) {
+                force_rows_items_kernel<true><<<ITEM_CTAS, RB_THREADS, sizeof(ForceRowsSmem), x>>>(sa, e->grid, e->consts);
+                cudaEventRecord(e->ev_join[1], x);
+                force_rows_kernel<true><<<grb, RB_THREADS, sizeof(ForceRowsSmem), s>>>(sa, e->grid, e->consts);
+            } else {
+                force_rows_items_kernel<false><<<ITEM_CTAS, RB_THREADS, sizeof(ForceRowsSmem), x>>>(sa, e->grid, e->consts);
+                cudaEventRecord(e->ev_join[1], x);
+                force_rows_kernel<false><<<grb, RB_THREADS, sizeof(ForceRowsSmem), s>>>(sa, e->grid, e->consts);
+            }
+            cudaStreamWaitEvent(s, e->ev_join[1], 0);
+        }
     } else {
         const int gsw = (n + SW_THREADS - 1) / SW_THREADS;
         if (stages & 2) density_kernel<<<gsw, SW_THREADS, 0, s>>>(sa, e->grid, e->consts);

@@ -23,9 +23,11 @@
 //     the reference's fp64 predicate inside the rounding band (rare, out of line) and accumulates the density in
 //     list order.  Lists leave as row slots of the force sweep's staging (force_rows_kernel, sweep_rows.cuh), packed in
 //     registers and written as 4 x 16 B per particle.
-// Tiles this kernel cannot take (Q2 grids, tiles whose rows or blocks exceed shared memory) are appended to a list and
-// processed by density_rows_fallback_kernel (the row-staged sweep of sweep_rows.cuh); single particles it cannot take
-// (aliased keys Q5, windows longer than FL_MAXR rounds) use the one-thread walk.  All paths produce the same bits.
+// Tiles this kernel cannot take run through the row-staged sweep of sweep_rows.cuh: tiles whose rows exceed the force
+// sweep's staging are split by rows_plan_kernel into 32-particle work items (density_rows_items_kernel on a second stream,
+// side by side with this kernel); Q2 grids and tiles whose blocks exceed this kernel's staging are appended to a second
+// list that density_rows_items_kernel runs afterwards.  Single particles it cannot take (aliased keys Q5, windows longer
+// than FL_MAXR rounds) use the one-thread walk.  All paths produce the same bits.
 #pragma once
 #include "sweep_rows.cuh"
 
@@ -74,8 +76,8 @@ static_assert(sizeof(FlatSmem) <= (228 / FL_CTAS - 1) * 1024, "FL_CTAS CTAs per 
 static_assert((3 * (FL_CAP + FL_SLACK) + FL_MAXR * 32) * 4 <= (int)sizeof(FlatSmem), "scan overrun must stay inside FlatSmem");
 
 struct FlatArgs {
-    int *refused;      // work left to density_rows_fallback_kernel: tile * 8 + (0: whole tile | 1 + pass)
-    int *n_refused;    // zeroed by rows_plan_kernel
+    int *refused;      // whole tiles handed over to density_rows_items_kernel: tile * 8
+    int *n_refused;    // zeroed by reorder_kernel
 };
 
 // Exact (slow, rare) evaluation of one particle's masks: fp64 predicate inside the rounding band, first 32 accepted,
@@ -120,6 +122,10 @@ density_flat_kernel(const SweepArgs a, const GridDesc g, const StepConsts c, con
     FlatSmem &sm = *reinterpret_cast<FlatSmem *>(smem_raw);
     const int j = threadIdx.x, lane = j & 31, warp = j >> 5;
     const int tile = blockIdx.x;
+    if (!g.aligned) {   // Q2 grid: every particle walks (row-staged sweep, whole tile)
+        if (j == 0) fa.refused[atomicAdd(fa.n_refused, 1)] = tile * 8;
+        return;
+    }
     const int p0 = tile * FL_THREADS;
     const int t = p0 + j;
     const int nb = min(FL_THREADS, a.n - p0);
@@ -166,21 +172,8 @@ density_flat_kernel(const SweepArgs a, const GridDesc g, const StepConsts c, con
     }
     if (ncell == 0) return;   // nothing alive in this tile
     const int ci = coff + __popc(bal & lanemask_le_()) - 1;
-    bool refuse = false;   // CTA-uniform
-    auto hand_over = [&]() {   // rows that fit the force sweep's staging: one item; else its four 32-particle passes
-        if (j == 0) {
-            if (!g.aligned || tp_fits) {
-                fa.refused[atomicAdd(fa.n_refused, 1)] = tile * 8;
-            } else {
-                const int q = atomicAdd(fa.n_refused, 4);
-                for (int u = 0; u < 4; ++u) fa.refused[q + u] = tile * 8 + 1 + u;
-            }
-        }
-    };
-    if (!g.aligned || !tp_fits || ncell > FL_MAXC) {
-        hand_over();
-        return;
-    }
+    if (!tp_fits) return;   // rows do not fit the force sweep's staging either: its passes are work items (rows_plan_kernel)
+    bool refuse = ncell > FL_MAXC;   // CTA-uniform (cannot happen while FL_MAXC == RB_MAXC: the plan fits)
     int cx = 0, cy = 0, cz = 0;
     if (live) decode_cell(g, key, cx, cy, cz);
     if (!refuse && first) {
@@ -272,8 +265,8 @@ density_flat_kernel(const SweepArgs a, const GridDesc g, const StepConsts c, con
         staged += sm.wsum2[w];
     }
     refuse = refuse || staged > FL_CAP;
-    if (refuse) {
-        hand_over();
+    if (refuse) {   // more blocks / staged candidates than this kernel holds: the row-staged sweep takes the whole tile
+        if (j == 0) fa.refused[atomicAdd(fa.n_refused, 1)] = tile * 8;
         return;
     }
     if (j < nblk) {

@@ -228,12 +228,13 @@ struct TilePlan {
 };
 
 constexpr int RP_WARPS = 8;
+constexpr int OWN_TILE = -2;         // only_pass value: the CTA's own tile (skipped if its rows do not fit: work items)
+constexpr int ITEM_CTAS = 148 * 2;   // grid of the work-item kernels
 
 __global__ void __launch_bounds__(RP_WARPS * 32)
 rows_plan_kernel(const SweepArgs a, const GridDesc g, TilePlan *__restrict__ plans, int ntiles,
-                 int *__restrict__ n_refused) {
+                 int *__restrict__ n_items, int *__restrict__ items) {
     const int lane = threadIdx.x & 31;
-    if (blockIdx.x == 0 && threadIdx.x == 0) *n_refused = 0;   // tile list of density_rows_fallback_kernel
     const int tile = blockIdx.x * RP_WARPS + (threadIdx.x >> 5);
     if (tile >= ntiles) return;
     const int p0 = tile * RB_THREADS;
@@ -284,7 +285,16 @@ rows_plan_kernel(const SweepArgs a, const GridDesc g, TilePlan *__restrict__ pla
     }
     if (lane == 0) {
         tp.slots = sum;
-        tp.fits = (sum <= RB_CAP && ncell <= RB_MAXC) ? 1 : 0;
+        const bool fits = sum <= RB_CAP && ncell <= RB_MAXC;
+        tp.fits = fits ? 1 : 0;
+        if (!fits && g.aligned) {
+            // rows that do not fit shared memory: both sweeps take the tile as 32-particle passes.  The passes become
+            // work items (tile * 8 + 1 + pass) that the first CTAs of the sweeps run before their own tile, so the
+            // long items start first and run side by side instead of one after the other inside one CTA.
+            const int np = (min(RB_THREADS, a.n - p0) + 31) / 32;
+            const int q = atomicAdd(n_items, np);   // zeroed by reorder_kernel
+            for (int u = 0; u < np; ++u) items[q + u] = tile * 8 + 1 + u;
+        }
     }
 }
 
@@ -445,6 +455,7 @@ __device__ __forceinline__ void density_rows_tile(const SweepArgs &a, const Grid
     {
         const TilePlan &tp = a.plans[tile];
         const bool plan_fits = g.aligned && tp.fits != 0 && tp.slots > 0;   // implies live particles
+        if (only_pass == OWN_TILE && g.aligned && tp.fits == 0) return;     // its passes are work items
         if (!plan_fits && __syncthreads_count(live) == 0) return;
     }
 
@@ -642,28 +653,29 @@ __device__ __forceinline__ void density_rows_tile(const SweepArgs &a, const Grid
     }
 }
 
+// Work items: the 32-particle passes of tiles whose rows do not fit (rows_plan_kernel) and whole tiles density_flat_kernel
+// hands over.  A small grid on a second, higher-priority stream runs them next to the main sweep, so the long items
+// start first and run side by side instead of one after the other inside one CTA of the main grid.
+__global__ void __launch_bounds__(RB_THREADS, RB_DENSITY_CTAS)
+density_rows_items_kernel(const SweepArgs a, const GridDesc g, const StepConsts c, const int *__restrict__ n_items,
+                          const int *__restrict__ items) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    DensityRowsSmem &sm = *reinterpret_cast<DensityRowsSmem *>(smem_raw);
+    const int n = *n_items;
+    for (int i = blockIdx.x; i < n; i += gridDim.x) {
+        const int item = items[i];   // tile * 8 + (0: whole tile | 1 + pass)
+        density_rows_tile(a, g, c, item >> 3, sm, (item & 7) - 1);
+        __syncthreads();
+        if (threadIdx.x == 0) mbar_inval(&sm.plan.mbar);   // the next item initialises it again
+        __syncthreads();
+    }
+}
+
 // Whole grid through the row-staged sweep (SPH_DENSITY=rows: A/B against density_flat_kernel of sweep_flat.cuh).
 __global__ void __launch_bounds__(RB_THREADS, RB_DENSITY_CTAS)
 density_rows_kernel(const SweepArgs a, const GridDesc g, const StepConsts c) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    density_rows_tile(a, g, c, blockIdx.x, *reinterpret_cast<DensityRowsSmem *>(smem_raw));
-}
-
-// The tiles density_flat_kernel left (Q2 grids, tiles whose rows / column blocks exceed its shared memory): a small
-// persistent grid runs down the list.
-__global__ void __launch_bounds__(RB_THREADS, RB_DENSITY_CTAS)
-density_rows_fallback_kernel(const SweepArgs a, const GridDesc g, const StepConsts c, const int *__restrict__ refused,
-                             const int *__restrict__ n_refused) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    DensityRowsSmem &sm = *reinterpret_cast<DensityRowsSmem *>(smem_raw);
-    const int n = *n_refused;
-    for (int i = blockIdx.x; i < n; i += gridDim.x) {
-        const int item = refused[i];   // tile * 8 + (0: whole tile | 1 + pass)
-        density_rows_tile(a, g, c, item >> 3, sm, (item & 7) - 1);
-        __syncthreads();
-        if (threadIdx.x == 0) mbar_inval(&sm.plan.mbar);   // the next tile initialises it again
-        __syncthreads();
-    }
+    density_rows_tile(a, g, c, blockIdx.x, *reinterpret_cast<DensityRowsSmem *>(smem_raw), OWN_TILE);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -671,25 +683,24 @@ density_rows_fallback_kernel(const SweepArgs a, const GridDesc g, const StepCons
 // (voxel_kernels.py:135-211, base_kernels.py:30-98), driven by the slot lists of density_rows_kernel.
 // ---------------------------------------------------------------------------------------------------------------------
 template <bool RECORD>
-__global__ void __launch_bounds__(RB_THREADS, RB_FORCE_CTAS)
-force_rows_kernel(const SweepArgs a, const GridDesc g, const StepConsts c) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    ForceRowsSmem &sm = *reinterpret_cast<ForceRowsSmem *>(smem_raw);
+__device__ __forceinline__ void force_rows_tile(const SweepArgs &a, const GridDesc &g, const StepConsts &c,
+                                                const int tile, ForceRowsSmem &sm, const int only_pass = -1) {
     RowPlan &plan = sm.plan;
     const int j = threadIdx.x;
-    const int p0 = blockIdx.x * RB_THREADS;
+    const int p0 = tile * RB_THREADS;
     const int t = p0 + j;
     const int nb = min(RB_THREADS, a.n - p0);
     const uint32_t key = (j < nb) ? a.skeys[t] : (uint32_t)g.ncells;
     const bool live = key != (uint32_t)g.ncells;
-    if ((j >> 5) == 0) rows_issue_planned<false>(a, g, plan, a.plans[blockIdx.x], sm.rpos, sm.rvel);
+    if ((j >> 5) == 0) rows_issue_planned<false>(a, g, plan, a.plans[tile], sm.rpos, sm.rvel);
     // issued before the key arrives (their use depends on it, their address does not)
     const uint8_t cf_raw = (j < nb) ? a.ncnt[t] : (uint8_t)0;
     const float rho_raw = (j < nb) ? a.srho[t] : 0.f;
     const uint32_t my_id = (j < nb) ? a.sids[t] : 0u;   // master slot of the epilogue's scatter
     __syncthreads();   // mbarrier initialised, row_lo / row_base of a planned tile published
     // a fitting plan implies live particles; otherwise count them (a tile of dead particles stages nothing)
-    const bool plan_fits = g.aligned && a.plans[blockIdx.x].fits != 0 && a.plans[blockIdx.x].slots > 0;
+    const bool plan_fits = g.aligned && a.plans[tile].fits != 0 && a.plans[tile].slots > 0;
+    if (only_pass == OWN_TILE && g.aligned && a.plans[tile].fits == 0) return;   // its passes are work items
     const bool any_live = plan_fits || __syncthreads_count(live) != 0;
 
     int cx = 0, cy = 0, cz = 0, my_cnt = 0;
@@ -704,14 +715,21 @@ force_rows_kernel(const SweepArgs a, const GridDesc g, const StepConsts c) {
             rho_i = rho_raw;
         }
     }
-    // dead particle: F = external force, rho = 0 (reference NaN semantics carry on); finished in the first trip
-    bool dead_todo = j < nb && !live;
+    // dead particle: F = external force, rho = 0 (reference NaN semantics carry on); finished in the first trip (of the
+    // pass that covers it)
+    bool dead_todo = j < nb && !live && (only_pass < 0 || (j >> 5) == only_pass);
 
     uint32_t parity = 0;
-    const bool tp_fits = g.aligned && any_live && a.plans[blockIdx.x].fits != 0;
+    const bool tp_fits = g.aligned && any_live && a.plans[tile].fits != 0;
     // -1: whole tile; 0..RB_WARPS-1: one warp's particles; RB_WARPS: no staging (Q2 grid: everyone walks; or nothing alive)
     int pass = (g.aligned && any_live) ? -1 : RB_WARPS;
     int j0 = 0, j1 = nb;
+    if (only_pass >= 0 && pass < 0) {
+        pass = only_pass;
+        j0 = pass * 32;
+        j1 = min(nb, j0 + 32);
+        if (j0 >= nb) return;
+    }
     for (;;) {
         // every path that completes a particle funnels into the ONE finish_particle call at the bottom of the trip
         ForceAcc f;
@@ -785,11 +803,34 @@ force_rows_kernel(const SweepArgs a, const GridDesc g, const StepConsts c) {
         }
         if (fin) finish_particle<RECORD>(a, c, t, pi, vi, rho_f, f, my_id);
 
-        if (pass >= RB_WARPS || (pass < 0 && tp_fits)) break;
+        if (pass >= RB_WARPS || (pass < 0 && tp_fits) || only_pass >= 0) break;
         ++pass;
         if (pass * 32 >= nb) break;
         j0 = pass * 32;
         j1 = min(nb, j0 + 32);
+        __syncthreads();
+    }
+}
+
+template <bool RECORD>
+__global__ void __launch_bounds__(RB_THREADS, RB_FORCE_CTAS)
+force_rows_kernel(const SweepArgs a, const GridDesc g, const StepConsts c) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    force_rows_tile<RECORD>(a, g, c, blockIdx.x, *reinterpret_cast<ForceRowsSmem *>(smem_raw), OWN_TILE);
+}
+
+// The passes of tiles whose rows do not fit (work items of rows_plan_kernel), next to force_rows_kernel.
+template <bool RECORD>
+__global__ void __launch_bounds__(RB_THREADS, RB_FORCE_CTAS)
+force_rows_items_kernel(const SweepArgs a, const GridDesc g, const StepConsts c) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    ForceRowsSmem &sm = *reinterpret_cast<ForceRowsSmem *>(smem_raw);
+    const int n = *a.n_items;
+    for (int i = blockIdx.x; i < n; i += gridDim.x) {
+        const int item = a.items[i];
+        force_rows_tile<RECORD>(a, g, c, item >> 3, sm, (item & 7) - 1);
+        __syncthreads();
+        if (threadIdx.x == 0) mbar_inval(&sm.plan.mbar);
         __syncthreads();
     }
 }
