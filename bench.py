@@ -9,9 +9,12 @@ sweep -> fused pressure/viscosity/integrate/collide sweep (reference: compute_ne
 sim/src/sph/strategies/abstract_sph_strategy.py:31-46).
 
 Workloads:
-    dam1m   BASELINE configs[1]: box dam-break column, 2^20 particles, fp32 engine          (default at N = 1)
-    box32m  BASELINE configs[3]: uniform box, 2^25 particles                               (default at N > 1)
-    pipe4m  BASELINE configs[2]: six-segment pipe, 2^22 particles, inflow/outflow recycle
+    box32m  BASELINE configs[3]: uniform box, 2^25 particles, 8 per cell -- the default at EVERY N (it fits one GPU), so
+            the 1 -> 8 GPU scaling curve is one workload
+    dam1m   BASELINE configs[1]: box dam-break column, 2^20 particles -- at N = 1 a second record of the same line
+            (`secondary.dam1m`: value, roofline, e2e, and the 1000-step straight-through run with dead / non-finite
+            counts next to the oracle's)
+    pipe4m  BASELINE configs[2]: six-segment pipe, 2^22 particles, inflow/outflow recycle (--workload pipe4m)
 
 Window: the reference's Voxel physics diverges within ~10 steps on every workload (fp64 oracle: |v| ~ 1e21 by step
 10, most particles NaN by step 40 -- DESIGN.md "Workloads"), after which a step is mostly dead particles.  So every
@@ -142,17 +145,33 @@ def peaks():
 
 
 WINDOW = 4
+DEFAULT_WORKLOAD = "box32m"   # BASELINE configs[3]: the one workload every N runs (it fits one GPU), so the driver's
+                              # scaling efficiency compares like with like; dam1m (configs[1]) rides along at N = 1
 
 
-def cpu_baseline(params, st, mode, window, budget_s=12.0):
-    """Oracle port (fp64, OpenMP) on the host cores, bounded sample of the same workload: the first steps of it."""
+def shared_config(name: str, desc: str, n: int, window: int) -> dict:
+    """The `config` object of the JSON line: identical in both arms (b200 / reference) and at every N."""
+    return {"workload": desc, "name": name, "particles": n,
+            "window": f"steps 1..{window} of the workload, start state restored in between (untimed)" if window
+            else "none: steps run straight through"}
+
+
+def _oracle(params, mode):
     from oracle import oracle as orc
     orc.set_exact_pow(False)
+    orc.set_num_threads(os.cpu_count() or 1)   # torchrun exports OMP_NUM_THREADS=1: the CPU arm uses every host core
     n = int(params.particle_count)
     pipe = params.pipe.to_numpy() if mode == "PIPE" else None
     P = orc.OracleParams(n=n, mode=mode, space=tuple(params.space_size), ext=tuple(params.external_force),
                          dt=1 / params.fps, pipe=pipe)
     rng = orc.rng_init(n) if mode == "PIPE" else None
+    return orc, P, rng
+
+
+def cpu_baseline(params, st, mode, window, budget_s=12.0):
+    """Oracle port (fp64, OpenMP) on the host cores, bounded sample of the same workload: the first steps of it."""
+    orc, P, rng = _oracle(params, mode)
+    n = int(params.particle_count)
     pos, vel = st.position, st.velocity
     el, steps = 0.0, 0
     while True:
@@ -172,81 +191,83 @@ def cpu_baseline(params, st, mode, window, budget_s=12.0):
 
 def run_reference_arm(args):
     """--impl reference: the reference's CPU path.  The reference is pure Python/numba and not installable on the box,
-    so this is the oracle port (oracle/sph_oracle.c) with all host threads, on the same config."""
+    so this is the oracle port (oracle/sph_oracle.c) with all host threads.  Every one of the K steps is a BOUNDED
+    SAMPLE of the workload: the same generator at the same particles-per-cell with fewer particles, sized so that
+    K + W steps take about two minutes (throughput per particle does not depend on the box size)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import oracle as orc
-    orc.set_exact_pow(False)
-    name = args.workload or ("dam1m" if args.gpus == 1 else "box32m")
-    params, st, mode, desc = make_workload(name, args.particles)
-    n = int(params.particle_count)
-    pipe = params.pipe.to_numpy() if mode == "PIPE" else None
-    P = orc.OracleParams(n=n, mode=mode, space=tuple(params.space_size), ext=tuple(params.external_force),
-                         dt=1 / params.fps, pipe=pipe)
-    rng = orc.rng_init(n) if mode == "PIPE" else None
-    pos, vel = st.position, st.velocity
-    # bounded: cap the total CPU time at ~150 s by shrinking the number of timed steps if one step is slow
+    name = args.workload or DEFAULT_WORKLOAD
+    full_n = args.particles or {"dam1m": 1 << 20, "box32m": 1 << 25, "pipe4m": 1 << 22}[name]
+    K, W = args.steps, max(args.warmup, 1)
+    # calibrate on a small sample, then size the sample for ~120 s in total
+    cal_n = min(full_n, 1 << 18)
+    params, st, mode, _ = make_workload(name, cal_n)
+    orc, P, rng = _oracle(params, mode)
+    orc.step(P, st.position, st.velocity, rng=rng, light=True)
     t0 = time.perf_counter()
-    r = orc.step(P, pos, vel, rng=rng, light=True)
-    pos, vel = r.position, r.velocity
-    one = time.perf_counter() - t0
-    warm = max(0, min(args.warmup, int(20.0 / max(one, 1e-9))) - 1)
-    steps = max(1, min(args.steps, int(150.0 / max(one, 1e-9))))
-    for _ in range(warm):
+    orc.step(P, st.position, st.velocity, rng=rng, light=True)
+    rate = cal_n / (time.perf_counter() - t0)
+    n = full_n
+    while n > cal_n and n * (K + W) / rate > 120.0:
+        n //= 2
+    params, st, mode, _ = make_workload(name, n)
+    _, _, _, desc = make_workload_desc(name, full_n)
+    orc, P, rng = _oracle(params, mode)
+    pos, vel = st.position, st.velocity
+    for i in range(W):
+        if args.window and i % args.window == 0:
+            pos, vel = st.position, st.velocity
         r = orc.step(P, pos, vel, rng=rng, light=True)
         pos, vel = r.position, r.velocity
     el = 0.0
-    for i in range(steps):
+    for i in range(K):
         if args.window and i % args.window == 0:
             pos, vel = st.position, st.velocity
         t0 = time.perf_counter()
         r = orc.step(P, pos, vel, rng=rng, light=True)
         el += time.perf_counter() - t0
         pos, vel = r.position, r.velocity
-    value = n * steps / el
-    sample = (f"{steps} timed full steps (of {args.steps} requested; bounded to ~150 s) after {warm + 1} warm-up, "
-              f"same workload N={n}, steps 1..{args.window or steps} from its start state")
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-            "warmup": warm + 1, "ms_per_step": el / steps * 1e3, "higher_is_better": True, "scaling": "strong",
+    value = n * K / el
+    sample = (f"each of the {K} timed steps (after {W} warm-up) is one full step over {n} particles of the same generator "
+              f"and density ({n}/{full_n} of the workload's particles), steps 1..{args.window or K} from its start "
+              f"state; fp64 C/OpenMP restatement oracle/sph_oracle.c")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": K,
+            "warmup": W, "ms_per_step": el / K * 1e3, "sample_particles": n, "higher_is_better": True,
+            "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": desc, "name": name, "particles": n, "window": args.window},
+            "config": shared_config(name, desc, full_n, args.window),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": orc.num_threads(), "kind": "port",
                              "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
-def run_gpu_arm(args):
+def make_workload_desc(name: str, n: int):
+    """Description string of a workload without generating it (the reference arm names the FULL workload)."""
+    from cuda_sph_b200 import config, workloads
+    if name == "dam1m":
+        d = workloads.cubic_dims(n, 2.5)
+        return None, None, "BOX", f"box dam-break column (first 10% of x, ~25/cell), N={n}, box {d * config.INF_R:.0f}^3"
+    if name == "box32m":
+        d = workloads.cubic_dims(n, 8.0)
+        return None, None, "BOX", f"uniform box 8 particles/cell, N={n}, box {d * config.INF_R:.0f}^3"
+    params, st, mode, desc = make_workload(name, n)
+    return None, None, mode, desc
+
+
+def measure_single(name, args, local_rank, stream, flush, *, K, W, e2e_steps, with_cpu):
+    """One workload on one GPU: value (device-resident, L2 flushed between steps), stage times + roofline of the
+    dominant kernel, e2e through compute_next_state, CPU baseline."""
     import torch
-    import torch.distributed as dist
     from cuda_sph_b200 import B200SPHStrategy, SphConstants
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-
-    if world > 1:
-        from cuda_sph_b200 import bench_multi
-        return bench_multi.run(args, rank, world, local_rank)
-
-    name = args.workload or "dam1m"
-    params, st, mode, desc = make_workload(name, args.particles)
+    params, st, mode, desc = make_workload(name, args.particles if name == (args.workload or DEFAULT_WORKLOAD) else None)
     n = int(params.particle_count)
-    stream = torch.cuda.Stream()
     s = B200SPHStrategy(params, SphConstants(mode=mode), device=local_rank, cuda_stream=stream.cuda_stream)
     s.upload(st)
     s.save_state()
     s.synchronize()
     window = args.window
-
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-    K, W = args.steps, max(args.warmup, 3)
 
     def flush_l2():
         with torch.cuda.stream(stream):
@@ -276,8 +297,7 @@ def run_gpu_arm(args):
     torch.cuda.synchronize()
     t_wall = time.perf_counter() - t_wall0
     launches = s.launch_count() - launches0
-    ms_steps = [a.elapsed_time(b) for a, b in zip(starts, ends)]
-    ms_total = float(sum(ms_steps))
+    ms_total = float(sum(a.elapsed_time(b) for a, b in zip(starts, ends)))
     value = n * K / (ms_total * 1e-3)
 
     # back-to-back (no flush) for context: groups of `window` steps, events around each group
@@ -294,7 +314,6 @@ def run_gpu_arm(args):
         torch.cuda.synchronize()
         hot_ms += e0.elapsed_time(e1)
         done += g_
-    value_hot = n * K / (hot_ms * 1e-3)
     clocks = sampler.stop()
     stats = s.stats()
 
@@ -329,7 +348,7 @@ def run_gpu_arm(args):
                          "peak_source": "148 SMs x 4 issue slots x 1.965 GHz"}
     except Exception:
         pass
-    kname = {"density": "density_rows_kernel", "force": "force_rows_kernel"}.get(dom, dom + "_kernel")
+    kname = {"density": "density_flat_kernel", "force": "force_rows_kernel"}.get(dom, dom + "_kernel")
     roofline = {"bound": "hbm", "kernel": kname, "achieved": stage_gbs[dom], "peak": hbm_peak,
                 "unit": "GB/s", "frac": stage_gbs[dom] / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": stage_bytes[dom] * n, "issue_roofline": issue,
@@ -337,63 +356,148 @@ def run_gpu_arm(args):
                 "stages_ms": stage_ms, "stages_gbs": stage_gbs,
                 "step_bytes_per_particle": sum(stage_bytes.values()),
                 "step_frac": sum(stage_bytes.values()) * value / 1e9 / hbm_peak,
-                "note": "neighbour sweeps are FP32-issue / shared-memory / latency bound at >2 particles/cell "
-                        "(SURVEY 8d; ncu: 1-8 % DRAM throughput), the HBM fraction is reported as the contract asks; "
-                        "traffic exceeds the algorithmic bytes because the neighbour lists (64 B/particle) and pair "
-                        "factors are engine-internal"}
+                "note": "the neighbour sweeps are bound by instruction issue and shared-memory return bandwidth at > 2 "
+                        "particles/cell (SURVEY 8d; ncu: 2-15 % DRAM throughput); the HBM fraction is reported as the "
+                        "contract asks; kernel_ms of the density stage includes its row-plan kernel; traffic exceeds the "
+                        "algorithmic bytes because the neighbour lists (64 B/particle) and pair factors are "
+                        "engine-internal"}
 
     # ---- e2e: compute_next_state through the C ABI with pinned fp64 host buffers ----------------------------------
-    def pinned(shape):
-        return torch.empty(shape, dtype=torch.float64, pin_memory=True).numpy()
+    e2e = None
+    if e2e_steps > 0:
+        def pinned(shape):
+            return torch.empty(shape, dtype=torch.float64, pin_memory=True).numpy()
 
-    hp, hv = pinned((n, 3)), pinned((n, 3))
-    op, ov, orho = pinned((n, 3)), pinned((n, 3)), pinned((n,))
-    KE = min(K, 48)
-    e2e_s = 0.0
-    for i in range(-3, KE):          # 3 untimed warm-up calls
-        if i <= 0 or (window and i % window == 0):
-            hp[:], hv[:] = st.position, st.velocity     # back to the start state (host side, untimed)
-        t0 = time.perf_counter()
-        s.compute_next_state_into(hp, hv, op, ov, orho)
-        if i >= 0:
-            e2e_s += time.perf_counter() - t0
-        hp, op = op, hp
-        hv, ov = ov, hv
-    e2e = {"value": n * KE / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 48 * n, "d2h_bytes_per_step": 56 * n,
-           "steps": KE, "ms_per_step": e2e_s / KE * 1e3,
-           "api": "B200SPHStrategy.compute_next_state_into -> sph_compute_next_state (fp64 pinned host buffers)"}
+        hp, hv = pinned((n, 3)), pinned((n, 3))
+        op, ov, orho = pinned((n, 3)), pinned((n, 3)), pinned((n,))
+        KE = min(K, e2e_steps)
+        nwarm = 3 if n <= (1 << 22) else 1
+        e2e_s = 0.0
+        for i in range(-nwarm, KE):          # untimed warm-up calls
+            if i <= 0 or (window and i % window == 0):
+                hp[:], hv[:] = st.position, st.velocity     # back to the start state (host side, untimed)
+            t0 = time.perf_counter()
+            s.compute_next_state_into(hp, hv, op, ov, orho)
+            if i >= 0:
+                e2e_s += time.perf_counter() - t0
+            hp, op = op, hp
+            hv, ov = ov, hv
+        e2e = {"value": n * KE / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 48 * n, "d2h_bytes_per_step": 56 * n,
+               "steps": KE, "ms_per_step": e2e_s / KE * 1e3,
+               "api": "B200SPHStrategy.compute_next_state_into -> sph_compute_next_state (fp64 pinned host buffers)"}
+        del hp, hv, op, ov, orho
 
-    # ---- CPU baseline beside it ---------------------------------------------------------------------------------
-    cpu = None
-    if not args.no_cpu_baseline:
-        cpu = cpu_baseline(params, st, mode, window)
+    cpu = cpu_baseline(params, st, mode, window) if with_cpu else None
+    out = {"name": name, "desc": desc, "n": n, "mode": mode, "value": value, "ms_per_step": ms_total / K,
+           "value_no_flush": n * K / (hot_ms * 1e-3), "wall_s": t_wall, "clocks": clocks, "launches": int(launches),
+           "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu,
+           "state": {"n_dead": stats["n_dead"], "n_nonfinite": stats["n_nonfinite"],
+                     "max_density": stats["max_density"], "steps_done": stats["steps_done"]}}
+    return out, s, (params, st, mode)
 
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": K, "warmup": W,
-            "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": desc, "name": name, "particles": n, "parallelism": "1 GPU",
-                       "window": f"state restored to the start state every {window} steps (untimed D2D copy)"
-                       if window else "none: steps run straight through",
-                       "l2": "flushed between steps (256 MiB memset), per-step CUDA events summed",
-                       "timing": "CUDA events on the engine stream"},
-            "value_no_flush": value_hot, "wall_s_timed_region": t_wall,
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-            "cpu_baseline": cpu,
-            "state": {"n_dead": stats["n_dead"], "n_nonfinite": stats["n_nonfinite"],
-                      "max_density": stats["max_density"], "steps_done": stats["steps_done"]}}
-    print(json.dumps(line), flush=True)
+
+def straight_through(s, params, st, mode, steps, oracle_steps=5):
+    """BASELINE configs[1] as written: `steps` steps straight through (no window), throughput by CUDA events around the
+    whole run, dead / non-finite particle counts along the way and -- for the first steps -- next to the fp64 oracle's."""
+    import torch
+    n = int(params.particle_count)
+    s.upload(st)
+    s.synchronize()
+    counts = []
+    orc, P, rng = _oracle(params, mode)
+    pos, vel = st.position, st.velocity
+    for k in range(oracle_steps):
+        s.step(1)
+        r = orc.step(P, pos, vel, rng=rng, light=True)
+        pos, vel = r.position, r.velocity
+        stt = s.stats()
+        counts.append({"step": k + 1, "engine_nonfinite": int(stt["n_nonfinite"]), "engine_dead": int(stt["n_dead"]),
+                       "oracle_nonfinite": int((~(np.isfinite(pos).all(axis=1) & np.isfinite(vel).all(axis=1))).sum())})
+    s.upload(st)
+    s.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ms, done, trace = 0.0, 0, []
+    while done < steps:
+        g_ = min(100, steps - done)
+        torch.cuda.synchronize()
+        e0.record()
+        s.step(g_)
+        e1.record()
+        torch.cuda.synchronize()
+        ms += e0.elapsed_time(e1)
+        done += g_
+        stt = s.stats()
+        trace.append({"step": done, "nonfinite": int(stt["n_nonfinite"]), "dead": int(stt["n_dead"])})
+    return {"steps": steps, "value": n * steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps,
+            "first_steps_vs_oracle": counts, "every_100_steps": trace,
+            "note": "no window: the reference's physics diverges (DESIGN.md section 6), later steps are increasingly dead "
+                    "or wall-piled particles; reported beside the windowed headline, not instead of it"}
+
+
+def run_gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        from cuda_sph_b200 import bench_multi
+        return bench_multi.run(args, rank, world, local_rank)
+
+    name = args.workload or DEFAULT_WORKLOAD
+    stream = torch.cuda.Stream()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    K, W = args.steps, max(args.warmup, 3)
+    main, s, _ = measure_single(name, args, local_rank, stream, flush, K=K, W=W,
+                                e2e_steps=48 if name != "box32m" else 8, with_cpu=not args.no_cpu_baseline)
     s.close()
+    del s
+    torch.cuda.empty_cache()
+
+    secondary = None
+    if name == DEFAULT_WORKLOAD and not args.no_secondary:
+        # BASELINE configs[1] (dam1m) beside the headline: same measurement, its own roofline, and the 1000-step run
+        sec, s2, (p2, st2, m2) = measure_single("dam1m", args, local_rank, stream, flush, K=max(K, 20), W=W,
+                                                e2e_steps=20, with_cpu=False)
+        sec["straight_through"] = straight_through(s2, p2, st2, m2, args.straight_steps)
+        s2.close()
+        secondary = {"dam1m": {"config": shared_config("dam1m", sec["desc"], sec["n"], args.window),
+                               "value": sec["value"], "unit": UNIT, "ms_per_step": sec["ms_per_step"],
+                               "value_no_flush": sec["value_no_flush"], "e2e": sec["e2e"], "roofline": sec["roofline"],
+                               "gpu_launches": sec["launches"], "state": sec["state"],
+                               "straight_through": sec["straight_through"]}}
+
+    line = {"metric": METRIC, "value": main["value"], "unit": UNIT, "n_gpus": 1, "steps": K, "warmup": W,
+            "ms_per_step": main["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": shared_config(name, main["desc"], main["n"], args.window),
+            "run": {"parallelism": "1 GPU",
+                    "l2": "flushed between steps (256 MiB memset), per-step CUDA events summed",
+                    "timing": "CUDA events on the engine stream"},
+            "value_no_flush": main["value_no_flush"], "wall_s_timed_region": main["wall_s"],
+            "clocks": main["clocks"], "e2e": main["e2e"], "gpu_launches": main["launches"],
+            "roofline": main["roofline"], "cpu_baseline": main["cpu_baseline"], "state": main["state"],
+            "secondary": secondary}
+    print(json.dumps(line), flush=True)
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=None, choices=[None, "dam1m", "box32m", "pipe4m"])
     ap.add_argument("--particles", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="N = 1: skip the dam1m record beside the headline")
+    ap.add_argument("--straight-steps", type=int, default=1000,
+                    help="steps of the straight-through dam1m run in the secondary record (BASELINE configs[1])")
     ap.add_argument("--no-single", action="store_true", help="multi-GPU: skip the 1-GPU run of the same workload")
     ap.add_argument("--window", type=int, default=WINDOW,
                     help="restore the start state every WINDOW steps (0 = never; see module docstring)")

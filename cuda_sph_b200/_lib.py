@@ -68,6 +68,7 @@ EXPORTS = {
     "sph_get_sorted_keys": (C.c_int, [_H, _P]),
     "sph_get_voxel_begin": (C.c_int, [_H, _P, C.c_int64]),
     "sph_get_neighbour_counts": (C.c_int, [_H, _P]),
+    "sph_get_neighbour_lists": (C.c_int, [_H, _P]),
     "sph_get_forces": (C.c_int, [_H, _P]),
     "sph_get_terms": (C.c_int, [_H, _P, _P]),
     "sph_get_rng_states": (C.c_int, [_H, _P]),

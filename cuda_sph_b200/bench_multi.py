@@ -18,7 +18,7 @@ def run(args, rank, world, local_rank):
     from .slab import NativeSlabRunner, balanced_bounds
     from .strategy import B200SPHStrategy, SphConstants
 
-    name = args.workload or "box32m"
+    name = args.workload or bench.DEFAULT_WORKLOAD
     params, st, mode, desc = bench.make_workload(name, args.particles)
     n = int(params.particle_count)
     voxel_x = float(params.voxel_size[0])
@@ -32,8 +32,10 @@ def run(args, rank, world, local_rank):
     K, W = args.steps, max(args.warmup, 3)
     dev = torch.device("cuda", local_rank)
 
-    # ---- single-GPU reference point on the same workload (rank 0 only, short) ----
-    single = None
+    # ---- single-GPU reference point on the same workload (rank 0 only, short): its throughput, and its state after one
+    #      window for the bitwise parity check of the slab run below ----
+    single, ref_state = None, None
+    pw = window or 4
     if rank == 0 and not args.no_single:
         s1 = B200SPHStrategy(params, SphConstants(mode=mode), device=local_rank)
         s1.upload(st)
@@ -43,13 +45,13 @@ def run(args, rank, world, local_rank):
         tot = 0.0
         for _ in range(2):
             s1.restore_state()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s1.synchronize()
             t0 = time.perf_counter()
-            s1.step(window or 4)
+            s1.step(pw)
             s1.synchronize()
             tot += time.perf_counter() - t0
-        single = n * 2 * (window or 4) / tot
+        single = n * 2 * pw / tot
+        ref_state = s1.download(np.float32)
         s1.close()
         del s1
         torch.cuda.empty_cache()
@@ -82,6 +84,21 @@ def run(args, rank, world, local_rank):
             restore()
         run_.step(g)
         done += g
+    # ---- parity: the state after one window, gathered by global id, must equal the 1-GPU engine's bit for bit ----
+    parity = None
+    if not args.no_single:
+        restore()
+        run_.step(pw)
+        gp, gv, grho = run_.gather_global(n)
+        if rank == 0:
+            def same(a_, b_):
+                a_, b_ = np.asarray(a_, np.float32), np.asarray(b_, np.float32)
+                return bool(np.all((a_ == b_) | (np.isnan(a_) & np.isnan(b_))))
+            parity = {"steps": pw, "position": same(gp, ref_state.position), "velocity": same(gv, ref_state.velocity),
+                      "density": same(grho, ref_state.density)}
+            parity["bitwise_equal"] = parity["position"] and parity["velocity"] and parity["density"]
+        del gp, gv, grho
+        ref_state = None
     sampler = bench.ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -163,13 +180,13 @@ def run(args, rank, world, local_rank):
         line = {"metric": bench.METRIC, "value": value, "unit": bench.UNIT, "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
-                "config": {"workload": desc, "name": name, "particles": n,
-                           "parallelism": f"x-slabs x{world}, 2-column ghost halos + migration: one fixed-size all_to_all per step "
-                                          "(NCCL), device-side routing, no host sync in the step loop",
-                           "slab_bounds": bounds, "capacity_per_rank": capacity,
-                           "window": f"state restored to the start state every {window} steps (untimed)"
-                           if window else "none", "l2": "working set per GPU larger than L2: no flush",
-                           "timing": "CUDA events per window, max over ranks, barrier + synchronize on both sides"},
+                "config": bench.shared_config(name, desc, n, window),
+                "run": {"parallelism": f"x-slabs x{world}, 2-column ghost halos + migration: one fixed-size all_to_all "
+                                       "per step (NCCL), device-side routing, no host sync in the step loop",
+                        "slab_bounds": bounds, "capacity_per_rank": capacity,
+                        "l2": "working set per GPU larger than L2: no flush",
+                        "timing": "CUDA events per window, max over ranks, barrier + synchronize on both sides"},
+                "parity_vs_1gpu": parity,
                 "wall_s_timed_region": t_wall, "clocks": clocks, "gpu_launches": int(launches.item()),
                 "e2e": e2e, "roofline": roofline, "cpu_baseline": None,
                 "value_1gpu_same_workload": single,

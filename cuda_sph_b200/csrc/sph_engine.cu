@@ -94,6 +94,7 @@ struct SphEngine {
     // snapshot (sph_save_state)
     float4 *snap_pos = nullptr, *snap_vel = nullptr;
     uint64_t *snap_rng = nullptr;
+    int64_t snap_rng_count = 0;
     int64_t snap_steps = -1;
     // graph
     cudaGraph_t graph = nullptr;
@@ -466,6 +467,32 @@ static int download_impl(SphEngine *e, T *pos, T *vel, T *rho) {
 int sph_download(sph_handle_t e, double *p, double *v, double *r) { return download_impl<double>(e, p, v, r); }
 int sph_download_f32(sph_handle_t e, float *p, float *v, float *r) { return download_impl<float>(e, p, v, r); }
 
+static SweepArgs sweep_args(SphEngine *e, const uint32_t *sids, int n, int n_own) {
+    SweepArgs sa{};
+    sa.spos = e->spos;
+    sa.svel = e->svel;
+    sa.skeys = e->skeys;
+    sa.sids = sids;
+    sa.cell_range = e->cell_range;
+    sa.srho = e->srho;
+    sa.nlist = e->nlist;
+    sa.ncnt = e->ncnt;
+    sa.pos_m = e->pos_m;
+    sa.vel_m = e->vel_m;
+    sa.sforce = e->sforce;
+    sa.spress = e->spress;
+    sa.svisc = e->svisc;
+    sa.pipe = e->pipe_d;
+    sa.rng = e->rng;
+    sa.gid = e->slab ? e->gid : nullptr;
+    sa.n = n;
+    sa.n_own = n_own;
+    sa.plans = e->tile_plans;
+    sa.n_items = e->refused;
+    sa.items = e->refused + 2;
+    return sa;
+}
+
 // Enqueue one step on e->stream.  If evs != nullptr, records stage boundaries into e->ev[0..5].
 // Enqueue one step on e->stream; `stages` selects parts of it (1: hash + sort, 2: cell table + reorder + row plans +
 // density sweep, 4: force sweep) so that sph_compute_next_state can interleave them with its host copies.
@@ -546,28 +573,7 @@ static int enqueue_step(SphEngine *e, bool timed, int n, int n_own, int stages =
     }
     if ((stages & 4) && split_vel) gather_vel_kernel<<<g256, 256, 0, s>>>(sids, e->vel_m, e->svel, n);
     if (timed) cudaEventRecord(e->ev[3], s);
-    SweepArgs sa{};
-    sa.spos = e->spos;
-    sa.svel = e->svel;
-    sa.skeys = e->skeys;
-    sa.sids = sids;
-    sa.cell_range = e->cell_range;
-    sa.srho = e->srho;
-    sa.nlist = e->nlist;
-    sa.ncnt = e->ncnt;
-    sa.pos_m = e->pos_m;
-    sa.vel_m = e->vel_m;
-    sa.sforce = e->sforce;
-    sa.spress = e->spress;
-    sa.svisc = e->svisc;
-    sa.pipe = e->pipe_d;
-    sa.rng = e->rng;
-    sa.gid = e->slab ? e->gid : nullptr;
-    sa.n = n;
-    sa.n_own = n_own;
-    sa.plans = e->tile_plans;
-    sa.n_items = e->refused;
-    sa.items = e->refused + 2;
+    const SweepArgs sa = sweep_args(e, sids, n, n_own);
     if (e->rows_sweeps) {
         const int grb = (n + RB_THREADS - 1) / RB_THREADS;
         cudaStream_t x = e->aux_stream;
@@ -642,8 +648,10 @@ int sph_step(sph_handle_t e, int32_t n_steps) {
             const int rc = enqueue_step(e, false, e->n, e->n);
             cudaGraph_t g = nullptr;
             cudaError_t ce = cudaStreamEndCapture(e->stream, &g);
-            if (rc) return 1;
-            if (ce != cudaSuccess) return fail(std::string("graph capture: ") + cudaGetErrorString(ce));
+            if (rc || ce != cudaSuccess) {
+                if (g) cudaGraphDestroy(g);
+                return rc ? 1 : fail(std::string("graph capture: ") + cudaGetErrorString(ce));
+            }
             e->graph = g;
             CK(cudaGraphInstantiate(&e->graph_exec, e->graph, 0));
             e->graph_valid = true;
@@ -742,11 +750,18 @@ int sph_save_state(sph_handle_t e) {
     const size_t n = e->n;
     if (!e->snap_pos) CK(cudaMalloc((void **)&e->snap_pos, sizeof(float4) * n));
     if (!e->snap_vel) CK(cudaMalloc((void **)&e->snap_vel, sizeof(float4) * n));
-    if (e->rng && !e->snap_rng) CK(cudaMalloc((void **)&e->snap_rng, 2 * sizeof(uint64_t) * n));
+    const size_t rng_bytes = 2 * sizeof(uint64_t) * (size_t)e->rng_count;   // slab mode: one state per GLOBAL particle
+    if (e->rng && e->snap_rng && e->snap_rng_count != e->rng_count) {
+        cudaFree(e->snap_rng);
+        e->snap_rng = nullptr;
+    }
+    if (e->rng && !e->snap_rng) {
+        CK(cudaMalloc((void **)&e->snap_rng, rng_bytes));
+        e->snap_rng_count = e->rng_count;
+    }
     CK(cudaMemcpyAsync(e->snap_pos, e->pos_m, sizeof(float4) * n, cudaMemcpyDeviceToDevice, e->stream));
     CK(cudaMemcpyAsync(e->snap_vel, e->vel_m, sizeof(float4) * n, cudaMemcpyDeviceToDevice, e->stream));
-    if (e->rng)
-        CK(cudaMemcpyAsync(e->snap_rng, e->rng, 2 * sizeof(uint64_t) * n, cudaMemcpyDeviceToDevice, e->stream));
+    if (e->rng) CK(cudaMemcpyAsync(e->snap_rng, e->rng, rng_bytes, cudaMemcpyDeviceToDevice, e->stream));
     e->snap_steps = e->steps_done;
     return 0;
 }
@@ -758,8 +773,9 @@ int sph_restore_state(sph_handle_t e) {
     const size_t n = e->n;
     CK(cudaMemcpyAsync(e->pos_m, e->snap_pos, sizeof(float4) * n, cudaMemcpyDeviceToDevice, e->stream));
     CK(cudaMemcpyAsync(e->vel_m, e->snap_vel, sizeof(float4) * n, cudaMemcpyDeviceToDevice, e->stream));
-    if (e->rng)
-        CK(cudaMemcpyAsync(e->rng, e->snap_rng, 2 * sizeof(uint64_t) * n, cudaMemcpyDeviceToDevice, e->stream));
+    if (e->rng && e->snap_rng && e->snap_rng_count == e->rng_count)
+        CK(cudaMemcpyAsync(e->rng, e->snap_rng, 2 * sizeof(uint64_t) * (size_t)e->rng_count, cudaMemcpyDeviceToDevice,
+                           e->stream));
     e->steps_done = e->snap_steps;
     return 0;
 }
@@ -1008,6 +1024,19 @@ int sph_get_neighbour_counts(sph_handle_t e, int32_t *counts) {
     CK(cudaGetLastError());
     return d2h(e, counts, e->stage, sizeof(int32_t) * (size_t)e->n);
 }
+int sph_get_neighbour_lists(sph_handle_t e, int32_t *lists) {
+    if (!e || !lists) return fail("null argument");
+    if (e->steps_done == 0) return fail("no step has run yet");
+    if (e->slab) return fail("the neighbour-list tap works on single-GPU handles");
+    if (!e->rows_sweeps) return fail("the neighbour-list tap needs the row-staged sweeps");
+    CK(cudaSetDevice(e->device));
+    const size_t bytes = sizeof(int32_t) * (size_t)e->n * kMaxNeighbours;
+    if (ensure_stage(e, std::max(bytes, 7 * sizeof(double) * (size_t)e->n))) return 1;
+    const SweepArgs sa = sweep_args(e, e->sids, e->n, e->n);
+    neighbour_lists_kernel<<<(e->n + 127) / 128, 128, 0, e->stream>>>(sa, e->grid, e->consts, (int32_t *)e->stage);
+    CK(cudaGetLastError());
+    return d2h(e, lists, e->stage, bytes);
+}
 static int get_vec3(SphEngine *e, const float4 *sorted, double *out) {
     CK(cudaSetDevice(e->device));
     if (ensure_stage(e, 7 * sizeof(double) * (size_t)e->n)) return 1;
@@ -1031,13 +1060,14 @@ int sph_get_terms(sph_handle_t e, double *pressure, double *viscosity) {
 int sph_get_rng_states(sph_handle_t e, uint64_t *states) {
     if (!e || !states) return fail("null argument");
     if (!e->rng) return fail("rng states exist in PIPE mode only");
-    return d2h(e, states, e->rng, 2 * sizeof(uint64_t) * (size_t)e->n);
+    return d2h(e, states, e->rng, 2 * sizeof(uint64_t) * (size_t)e->rng_count);
 }
 int sph_set_rng_states(sph_handle_t e, const uint64_t *states) {
     if (!e || !states) return fail("null argument");
     if (!e->rng) return fail("rng states exist in PIPE mode only");
     CK(cudaSetDevice(e->device));
-    CK(cudaMemcpyAsync(e->rng, states, 2 * sizeof(uint64_t) * (size_t)e->n, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(e->rng, states, 2 * sizeof(uint64_t) * (size_t)e->rng_count, cudaMemcpyHostToDevice,
+                       e->stream));
     CK(cudaStreamSynchronize(e->stream));
     return 0;
 }

@@ -812,6 +812,52 @@ __device__ __forceinline__ void force_rows_tile(const SweepArgs &a, const GridDe
     }
 }
 
+// Parity tap (voxel_kernels.py:78-85, `neighbours`): the lists of the most recent density sweep as PARTICLE IDS, id
+// order, -1 padded.  Particles of planned tiles are decoded from the slot lists the sweeps really used; walk-path
+// particles and tiles taken as 32-particle passes (pass-local slots) are re-walked.
+__global__ void __launch_bounds__(128)
+neighbour_lists_kernel(const SweepArgs a, const GridDesc g, const StepConsts c, int32_t *__restrict__ out) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= a.n) return;
+    const uint32_t key = a.skeys[t];
+    int32_t *row = out + (size_t)a.sids[t] * kMaxNeighbours;
+    for (int k = 0; k < kMaxNeighbours; ++k) row[k] = -1;
+    if (key == (uint32_t)g.ncells) return;
+    const TilePlan &tp = a.plans[t / RB_THREADS];
+    const uint8_t cf = a.ncnt[t];
+    if (g.aligned && tp.fits && !(cf & CNT_WALK)) {
+        int base[10];
+        base[0] = 0;
+        for (int r = 0; r < 9; ++r) base[r + 1] = base[r] + tp.row_len[r];
+        const uint16_t *lst = a.nlist + (size_t)t * kMaxNeighbours;
+        for (int k = 0; k < (int)cf; ++k) {
+            const int slot = lst[k];
+            int r = 0;
+            while (r < 8 && slot >= base[r + 1]) ++r;
+            row[k] = (int32_t)a.sids[tp.row_lo[r] + (slot - base[r])];
+        }
+        return;
+    }
+    const float4 pi = a.spos[t];
+    int vx, vy, vz, k = 0;
+    if (!cell_of(g, pi.x, pi.y, pi.z, vx, vy, vz)) return;
+    for (int dx = -1; dx <= 1; ++dx)
+        for (int dy = -1; dy <= 1; ++dy)
+            for (int dz = -1; dz <= 1; ++dz) {
+                const int x = vx + dx, y = vy + dy, z = vz + dz;
+                if (x < 0 || x >= g.tx || y < 0 || y >= g.ty || z < 0 || z >= g.tz) continue;
+                const long long cl = (long long)x - g.xoff + (long long)y * g.wn + (long long)z * g.wn * g.hn;
+                if (cl < 0 || cl >= g.ncells) continue;
+                const int2 r = __ldg(&a.cell_range[cl]);
+                for (int j = r.x; j < r.y; ++j) {
+                    const float4 pj = __ldg(&a.spos[j]);
+                    if (!in_range_exact(pi.x, pi.y, pi.z, pj.x, pj.y, pj.z, c.r2_max)) continue;
+                    row[k] = (int32_t)a.sids[j];
+                    if (++k >= kMaxNeighbours) return;
+                }
+            }
+}
+
 template <bool RECORD>
 __global__ void __launch_bounds__(RB_THREADS, RB_FORCE_CTAS)
 force_rows_kernel(const SweepArgs a, const GridDesc g, const StepConsts c) {

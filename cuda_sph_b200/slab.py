@@ -456,7 +456,7 @@ class NativeSlabRunner:
 
     def __init__(self, params, constants=None, *, col_hist: np.ndarray, bounds: Sequence[int], device: int = 0,
                  group=None, own_slack: float = 1.08, ghost_slack: float = 1.4, migrant_frac: float = 0.02,
-                 far_frac: float = 0.005, compact_every: int = 16):
+                 far_frac: float = 0.005, compact_every: int = 4, poll_every: int = 16):
         from . import _lib
         from .strategy import SphConstants
         self._lib = _lib.load()
@@ -473,7 +473,13 @@ class NativeSlabRunner:
         assert len(self.bounds) == self.world + 1 and self.bounds[0] == 0 and self.bounds[-1] == self.n_cols
         self.lo, self.hi = self.bounds[self.rank], self.bounds[self.rank + 1]
         self.n_global = int(params.particle_count)
+        # holes left by emigrants are closed every `compact_every` steps (device-side; inbound migrants take new slots
+        # above the high-water mark in between, so this bounds how far it can creep towards own_cap)
         self.compact_every = int(compact_every)
+        # the overflow word is reduced over the ranks and read back every `poll_every` steps WITHOUT blocking the step
+        # loop: the copy issued at one poll is looked at when the next one comes round
+        self.poll_every = int(poll_every)
+        self._poll = None
         pipe_mode = cst.mode.upper() == "PIPE"
 
         plan = plan_capacities(col_hist, self.bounds, self.rank, self.n_global, pipe_mode, own_slack=own_slack,
@@ -522,6 +528,7 @@ class NativeSlabRunner:
         self.V = view(1, (cap, 4), "<f4", torch.float32)
         self.G = view(4, (cap,), "<i4", torch.int32)
         self.counters = view(6, (8,), "<i4", torch.int32)
+        self.R = view(5, (self.n_global, 2), "<i8", torch.int64) if pipe_mode else None   # xoroshiro128+ states by global id
         self.steps = 0
 
     # ------------------------------------------------------------------ loading / stepping
@@ -561,6 +568,26 @@ class NativeSlabRunner:
             self.steps += 1
             if self.compact_every and self.steps % self.compact_every == 0:
                 self._chk(self._lib.sph_slab_compact(self._h))
+            if self.poll_every and self.steps % self.poll_every == 0:
+                self._poll_overflow()
+
+    def _poll_overflow(self) -> None:
+        """Sticky overflow check off the critical path.  A lost particle cannot be recovered, so this raises (on every
+        rank: the flag is max-reduced first) at the latest `poll_every` steps after the step that dropped it."""
+        if self._poll is not None:
+            host, ev = self._poll
+            ev.synchronize()          # recorded poll_every steps ago: long done
+            if int(host.item()):
+                raise RuntimeError(f"x-slab exchange overflow (flags {int(host.item())}, rank {self.rank}): particles "
+                                   "were dropped; raise own_slack / ghost_slack / migrant_frac / far_frac")
+        flag = self.counters[2:3].to(torch.int64)
+        if self.world > 1:
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=self.group)
+        host = torch.empty(1, dtype=torch.int64, pin_memory=True)
+        host.copy_(flag, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self._poll = (host, ev)
 
     def step_timed(self) -> dict:
         """One step with CUDA events around every phase (synchronises; for the breakdown in bench.py, not for `value`)."""
@@ -588,12 +615,17 @@ class NativeSlabRunner:
 
     # ------------------------------------------------------------------ snapshots (bench windows)
     def snapshot(self):
+        """Owned region + counters (+ the xoroshiro states in PIPE mode: they travel with the particles)."""
         return (self.P[:self.own_cap].clone(), self.V[:self.own_cap].clone(), self.G[:self.own_cap].clone(),
-                self.counters.clone())
+                self.counters.clone(), self.R.clone() if self.R is not None else None)
 
     def restore(self, snap) -> None:
         self.P[:self.own_cap], self.V[:self.own_cap], self.G[:self.own_cap] = snap[0], snap[1], snap[2]
+        overflow = self.counters[2].clone()     # sticky: a restore must not hide an overflow that already happened
         self.counters.copy_(snap[3])
+        self.counters[2] = torch.maximum(overflow, snap[3][2])
+        if snap[4] is not None:
+            self.R.copy_(snap[4])
 
     # ------------------------------------------------------------------ inspection (these synchronise)
     def status(self) -> dict:
@@ -653,7 +685,7 @@ class NativeSlabRunner:
 
     def close(self):
         if getattr(self, "_h", None):
-            self.P = self.V = self.G = self.counters = self.send = self.recv = None
+            self.P = self.V = self.G = self.R = self.counters = self.send = self.recv = None
             self._lib.sph_destroy(self._h)
             self._h = None
 

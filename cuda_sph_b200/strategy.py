@@ -99,7 +99,14 @@ class B200SPHStrategy:
         return self.new_state
 
     def compute_next_state_into(self, pos, vel, out_pos, out_vel, out_rho):
-        """Same, into caller-owned fp64 buffers (e.g. pinned memory); nothing is allocated."""
+        """Same, into caller-owned fp64 buffers (e.g. pinned memory); nothing is allocated.  The C ABI takes raw
+        pointers, so dtype, shape and contiguity are checked here."""
+        n = self.n
+        for name, arr, shape in (("pos", pos, (n, 3)), ("vel", vel, (n, 3)), ("out_pos", out_pos, (n, 3)),
+                                 ("out_vel", out_vel, (n, 3)), ("out_rho", out_rho, (n,))):
+            if not (isinstance(arr, np.ndarray) and arr.dtype == np.float64 and arr.shape == shape
+                    and arr.flags.c_contiguous):
+                raise ValueError(f"{name}: expected a C-contiguous float64 array of shape {shape}")
         _lib.check(self._lib.sph_compute_next_state(self._h, pos.ctypes.data, vel.ctypes.data, out_pos.ctypes.data,
                                                     out_vel.ctypes.data, out_rho.ctypes.data))
         self._force_stale = True
@@ -118,7 +125,8 @@ class B200SPHStrategy:
         pos, vel = np.asarray(state.position), np.asarray(state.velocity)
         if pos.dtype == np.float32 and vel.dtype == np.float32:
             pos, vel = np.ascontiguousarray(pos), np.ascontiguousarray(vel)
-            assert pos.shape == (n, 3) and vel.shape == (n, 3)
+            if pos.shape != (n, 3) or vel.shape != (n, 3):
+                raise ValueError(f"position / velocity must have shape ({n}, 3)")
             _lib.check(self._lib.sph_upload_f32(self._h, pos.ctypes.data, vel.ctypes.data))
         else:
             pos, vel = _f64(pos, (n, 3)), _f64(vel, (n, 3))
@@ -137,6 +145,9 @@ class B200SPHStrategy:
 
     def download(self, dtype=np.float64) -> SimulationState:
         n = self.n
+        dtype = np.dtype(dtype)
+        if dtype not in (np.dtype(np.float64), np.dtype(np.float32)):
+            raise ValueError("download() supports float64 and float32 only")
         pos, vel, rho = np.empty((n, 3), dtype), np.empty((n, 3), dtype), np.empty(n, dtype)
         fn = self._lib.sph_download if dtype == np.float64 else self._lib.sph_download_f32
         _lib.check(fn(self._h, pos.ctypes.data, vel.ctypes.data, rho.ctypes.data))
@@ -185,6 +196,13 @@ class B200SPHStrategy:
     def neighbour_counts(self):
         return self._i32(self._lib.sph_get_neighbour_counts, self.n)
 
+    def neighbour_lists(self) -> np.ndarray:
+        """(N, 32) int32: the neighbour lists of the most recent step as particle ids in list order, -1 padded
+        (`neighbours` of get_neighbours, voxel_kernels.py:29-85)."""
+        out = np.empty((self.n, 32), np.int32)
+        _lib.check(self._lib.sph_get_neighbour_lists(self._h, out.ctypes.data))
+        return out
+
     def terms(self):
         pr, vi = np.empty((self.n, 3)), np.empty((self.n, 3))
         _lib.check(self._lib.sph_get_terms(self._h, pr.ctypes.data, vi.ctypes.data))
@@ -197,7 +215,8 @@ class B200SPHStrategy:
 
     def set_rng_states(self, states):
         st = np.ascontiguousarray(states, np.uint64)
-        assert st.shape == (self.n, 2)
+        if st.shape != (self.n, 2):
+            raise ValueError(f"rng states must have shape ({self.n}, 2)")
         _lib.check(self._lib.sph_set_rng_states(self._h, st.ctypes.data))
 
     def stats(self) -> dict:

@@ -162,6 +162,8 @@ int sph_get_sorted_ids(sph_handle_t h, int32_t *ids);            /* voxel_partic
 int sph_get_sorted_keys(sph_handle_t h, int32_t *keys);          /* voxel_particle_map['voxel_id']           :85-88 */
 int sph_get_voxel_begin(sph_handle_t h, int32_t *begin, int64_t n_cells); /* self.voxel_begin (-1 = empty)  :92-107 */
 int sph_get_neighbour_counts(sph_handle_t h, int32_t *counts);   /* get_neighbours return value   voxel_kernels.py:85 */
+int sph_get_neighbour_lists(sph_handle_t h, int32_t *lists);     /* N x 32 particle ids, -1 padded: `neighbours` of
+                                                                    get_neighbours          voxel_kernels.py:29-85 */
 int sph_get_forces(sph_handle_t h, double *force);               /* self.result_force  abstract_sph_strategy.py:83 */
 int sph_get_terms(sph_handle_t h, double *pressure, double *viscosity); /* d_new_pressure_term / d_new_viscosity_term */
 int sph_get_rng_states(sph_handle_t h, uint64_t *states);        /* N x 2 uint64 (PIPE mode)                        */

@@ -345,3 +345,186 @@ def test_pipe_4m_single_step_properties():
     out = s.download()
     assert np.isfinite(out.density).all() and (out.density > 0).all()
     s.close()
+
+
+# ---- neighbour lists themselves (not only their counts) ---------------------------------------------------------------
+@pytest.mark.parametrize("name", ["kat4", "box_dense", "box_sparse", "box_medium"])
+def test_neighbour_lists_match_reference_golden(name):
+    """The lists the sweeps really used (slot lists decoded to particle ids) == the `neighbours` arrays the reference's
+    own get_neighbours wrote (voxel_kernels.py:29-85; tests/golden/generate_golden.py), entry for entry."""
+    from cuda_sph_b200.data_classes import SimulationState
+    g = load_golden(name)
+    n = len(g["pos_in"])
+    s = _strategy(n, "BOX", g["space"], g["voxel"], g["ext"], g["fps"])
+    s.compute_next_state(SimulationState(g["pos_in"], g["vel_in"], np.zeros(n)))
+    lists, cnt = s.neighbour_lists(), s.neighbour_counts()
+    assert np.array_equal(cnt, g["neigh_count"])
+    for i in range(n):
+        assert np.array_equal(lists[i, :cnt[i]], g["neighbours"][i, :cnt[i]]), i
+        assert (lists[i, cnt[i]:] == -1).all()
+    s.close()
+
+
+@pytest.mark.parametrize("maker,n,arg,seed", [("dam", 60000, 2.5, 51), ("box", 30000, 2.5, 52), ("box", 40000, 8.0, 53),
+                                              ("box", 40000, 60.0, 54)])
+def test_neighbour_lists_match_oracle(maker, n, arg, seed):
+    """Same at sizes the reference cannot run: capped lists (dam-break column), sparse lists, and 60 per cell where the
+    tiles are taken as 32-particle work items."""
+    from cuda_sph_b200 import workloads
+    from oracle import oracle as orc
+    params, st = (workloads.dam_break if maker == "dam" else workloads.uniform_box)(n, arg, seed)
+    s = _strategy(n, "BOX", params.space_size, params.voxel_size, params.external_force, params.fps)
+    s.compute_next_state(st)
+    P = orc.OracleParams(n=n, space=tuple(params.space_size), dt=1 / params.fps)
+    r = orc.step(P, st.position, st.velocity, want_neighbours=True)
+    assert np.array_equal(s.neighbour_counts(), r.neigh_count)
+    assert np.array_equal(s.neighbour_lists(), r.neighbours)
+    s.close()
+
+
+def _band_case(seed=61, n_bg=20000):
+    """Adversarial state for the fp64 predicate sqrt(r^2) <= h (voxel_kernels.py:20-26): shells of candidates at
+    r = h exactly, one fp32 ulp inside / outside, and at Pythagorean offsets whose fp32 squares sum to h^2 only up to
+    rounding (so fp64 decides) around several centres; one centre has 40 candidates just OUTSIDE in the first cell of its
+    walk, which exhausts the superset budget of the sweep and forces its exact re-walk."""
+    rng = np.random.default_rng(seed)
+    space = np.array([40.0, 40.0, 40.0])
+    bg = (rng.random((n_bg, 3), dtype=np.float32) * np.float32(40)).astype(np.float32)
+    h = np.float32(2.0)
+    quads = [(3, 4, 0, 5), (5, 12, 0, 13), (8, 15, 0, 17), (7, 24, 0, 25), (20, 21, 0, 29), (1, 2, 2, 3), (2, 3, 6, 7),
+             (1, 4, 8, 9), (4, 4, 7, 9), (2, 6, 9, 11), (6, 6, 7, 11), (3, 4, 12, 13), (2, 10, 11, 15), (1, 12, 12, 17)]
+    pts = []
+    centres = np.array([[11, 11, 11], [21.3, 20.7, 19.9], [1.0, 1.0, 1.0], [38.9, 38.8, 38.7], [15.5, 2.25, 30.125]],
+                       np.float32)
+    for c0 in centres:
+        pts.append(c0)
+        for (a, b, c_, d) in quads:
+            off = np.array([a, b, c_], np.float32) * (h / np.float32(d))
+            for perm in ((0, 1, 2), (1, 2, 0), (2, 0, 1)):
+                for sgn in ((1, 1, 1), (-1, 1, 1), (1, -1, -1), (-1, -1, 1)):
+                    pts.append(c0 + off[list(perm)] * np.array(sgn, np.float32))
+        for ax in range(3):
+            for sgn in (-1, 1):
+                e = np.zeros(3, np.float32)
+                e[ax] = sgn * h
+                on = c0 + e
+                pts += [on, np.nextafter(on, on + e).astype(np.float32), np.nextafter(on, c0).astype(np.float32)]
+    # 40 identical candidates one ulp outside, in the (dx = -1) cell the walk of centre 0 visits first
+    out = np.array([np.nextafter(np.float32(9.0), np.float32(0.0)), 11.0, 11.0], np.float32)
+    pts += [out] * 40
+    pts = np.asarray(pts, np.float32)
+    pts = pts[np.all((pts >= 0) & (pts < 40), axis=1)]
+    pos = np.concatenate([pts, bg]).astype(np.float64)
+    vel = rng.uniform(-3, 3, pos.shape).astype(np.float32).astype(np.float64)
+    return space, pos, vel
+
+
+def test_band_predicate_adversarial():
+    """Pairs at r = h, h +- 1 ulp(fp32) and at fp64-rounding distance from h: counts and LISTS equal the fp64 oracle's
+    (the in-band fp64 re-test, the in-place list compaction and the exhausted-superset re-walk are all exercised)."""
+    from cuda_sph_b200.data_classes import SimulationState
+    from oracle import oracle as orc
+    space, pos, vel = _band_case()
+    n = len(pos)
+    s = _strategy(n, "BOX", space, [2, 2, 2], [0, -2, 0], 20)
+    s.compute_next_state(SimulationState(pos, vel, np.zeros(n)))
+    P = orc.OracleParams(n=n, space=tuple(space), dt=1 / 20)
+    r = orc.step(P, pos, vel, want_neighbours=True)
+    # the case does contain band pairs on both sides of the predicate
+    d2 = ((pos[None, :400, :] - pos[:400, None, :]) ** 2).sum(-1)
+    assert ((np.abs(d2 - 4.0) < 4e-5) & (d2 <= 4.0)).sum() > 50 and ((np.abs(d2 - 4.0) < 4e-5) & (d2 > 4.0)).sum() > 50
+    assert np.array_equal(s.neighbour_counts(), r.neigh_count)
+    assert np.array_equal(s.neighbour_lists(), r.neighbours)
+    ref = dict(keys=r.keys, map_ids=r.map_ids, voxel_begin=r.voxel_begin, neigh_count=r.neigh_count, density=r.density,
+               pressure=r.pressure, viscosity=r.viscosity, force=r.force, vel_out=r.velocity, pos_out=r.position)
+    _check_against(s, ref)
+    s.close()
+
+
+@pytest.mark.parametrize("mode", ["BOX", "PIPE"])
+def test_aliased_keys_quirk_q5(mode):
+    """Positions outside the domain in y (y < -voxel, y >= space) and x >= space: the reference's key arithmetic aliases
+    them into other rows' cells (quirk Q5).  Such particles are candidates of the cell they alias into and walk their OWN
+    27 cells themselves -- one step vs the oracle, lists included."""
+    from cuda_sph_b200 import config
+    from cuda_sph_b200.data_classes import SimulationState
+    from oracle import oracle as orc
+    rng = np.random.default_rng(71)
+    n = 12000
+    if mode == "BOX":
+        space, table, ext = np.array([24.0, 24.0, 24.0]), None, [0, -2, 0]
+    else:
+        params = config.pipe_params(n)
+        space, table, ext = np.asarray(params.space_size, float), params.pipe.to_numpy(), params.external_force
+    pos = (rng.random((n, 3), dtype=np.float32) * space.astype(np.float32)).astype(np.float32)
+    k = n // 10
+    pos[:k, 1] = -rng.uniform(2.0, 5.9, k).astype(np.float32)                       # vy = -1, -2: alias into row H-1, H-2
+    pos[k:2 * k, 1] = (space[1] + rng.uniform(0.0, 3.9, k)).astype(np.float32)      # vy = H, H+1: alias into the next z slab
+    pos[2 * k:3 * k, 0] = (space[0] + rng.uniform(0.0, 3.9, k)).astype(np.float32)  # vx = W, W+1: alias into the next row
+    pos, vel = pos.astype(np.float64), rng.uniform(-3, 3, (n, 3)).astype(np.float32).astype(np.float64)
+    s = _strategy(n, mode, space, [2, 2, 2], ext, 20, table)
+    s.compute_next_state(SimulationState(pos, vel, np.zeros(n)))
+    P = orc.OracleParams(n=n, mode=mode, space=tuple(space), ext=tuple(ext), dt=1 / 20, pipe=table)
+    orng = orc.rng_init(n) if mode == "PIPE" else None
+    r = orc.step(P, pos, vel, rng=orng, want_neighbours=True)
+    assert np.array_equal(s.neighbour_counts(), r.neigh_count)
+    assert np.array_equal(s.neighbour_lists(), r.neighbours)
+    ref = dict(keys=r.keys, map_ids=r.map_ids, voxel_begin=r.voxel_begin, neigh_count=r.neigh_count, density=r.density,
+               pressure=r.pressure, viscosity=r.viscosity, force=r.force, vel_out=r.velocity, pos_out=r.position)
+    # a third of the particles sit outside the domain, so the rest is sparse and a few particles interact with a single
+    # neighbour inside the last 0.1 % of the support (rho ~ 1e-11, |F| ~ 1e15): there (h - r)^2 carries the fp32 rounding
+    # of r^2 (up to 5e-4 relative on those particles, every other one stays below 5e-5).  They are compared at 1e-3,
+    # everything else at the contract's 1e-4.
+    thin = (r.density < 1e-8) & (r.neigh_count >= 1)
+    for nb in r.neighbours[thin]:
+        thin[nb[nb >= 0]] = True     # the partner of such a pair sees the same term
+    assert thin.sum() < 20
+    keep = ~thin
+    out = s.new_state
+    pr, vi = s.terms()
+    fnorm = np.linalg.norm(r.force, axis=1)
+    for sel, tol in ((keep, VEC_RTOL), (thin, 1e-3)):
+        assert max_rel(out.density[sel], r.density[sel]) <= RHO_RTOL
+        assert vec_rel(pr[sel], r.pressure[sel], floor=fnorm[sel]) <= tol
+        assert vec_rel(vi[sel], r.viscosity[sel], floor=fnorm[sel]) <= tol
+        assert vec_rel(s.result_force[sel], r.force[sel]) <= tol
+        assert vec_rel(out.velocity[sel], r.velocity[sel]) <= tol
+        assert vec_rel(out.position[sel], r.position[sel]) <= tol
+    assert np.array_equal(s.keys(), r.keys) and np.array_equal(s.sorted_ids(), r.map_ids)
+    assert np.array_equal(s.voxel_begin(), r.voxel_begin)
+    if mode == "PIPE":
+        assert np.array_equal(s.rng_states(), orng)
+    s.close()
+
+
+@pytest.mark.parametrize("mode", ["BOX", "PIPE"])
+def test_save_restore_round_trip(mode):
+    """sph_save_state / sph_restore_state (the benchmark window depends on them): restoring and stepping again gives the
+    same bits, RNG states included in PIPE mode."""
+    from cuda_sph_b200 import workloads
+    n = 30000
+    if mode == "BOX":
+        params, st = workloads.dam_break(n, 2.5, seed=81)
+        table = None
+    else:
+        params, st = workloads.pipe_flow(n, seed=82)
+        table = params.pipe.to_numpy()
+        vel = np.random.default_rng(83).uniform(-30, 30, (n, 3)).astype(np.float32).astype(np.float64)
+        vel[: n // 10, 0] = 2000.0   # recycle through the outlet: the xoroshiro states advance
+        st = type(st)(st.position, vel, st.density)
+    s = _strategy(n, mode, params.space_size, params.voxel_size, params.external_force, params.fps, table)
+    s.upload(st)
+    s.step(2)
+    s.save_state()
+    rng0 = s.rng_states() if mode == "PIPE" else None
+    s.step(3)
+    a, rng_a = s.download(), (s.rng_states() if mode == "PIPE" else None)
+    s.restore_state()
+    if mode == "PIPE":
+        assert np.array_equal(s.rng_states(), rng0)
+    s.step(3)
+    b, rng_b = s.download(), (s.rng_states() if mode == "PIPE" else None)
+    assert same(a.position, b.position) and same(a.velocity, b.velocity) and same(a.density, b.density)
+    if mode == "PIPE":
+        assert np.array_equal(rng_a, rng_b) and not np.array_equal(rng_a, rng0)
+    s.close()

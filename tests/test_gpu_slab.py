@@ -94,3 +94,43 @@ def test_two_gpu_slabs_equal_single_gpu(tmp_path, mode, n, steps, extra, kind):
     assert eq(got["vel"], ref.velocity)
     assert eq(got["rho"], ref.density)
     assert got["halo"] > 0 and got["migrated"] > 0
+
+
+@pytest.mark.parametrize("mode,n,steps", [("BOX", 120000, 3), ("PIPE", 20000, 1)])
+def test_single_rank_native_slab_equals_plain_engine(mode, n, steps):
+    """World size 1 (runs on the driver's 1-GPU box): the slot layout with holes, slab_route / slab_unpack through the
+    self-exchange, the in-cell order repair by global id (fix_order_kernel) and the compaction must reproduce the plain
+    engine bit for bit -- BOX three steps (compaction after step 2), PIPE one step incl. the outlet -> inlet recycle."""
+    from cuda_sph_b200 import B200SPHStrategy, SphConstants
+    from cuda_sph_b200.slab import NativeSlabRunner
+    params, st = _case(mode, n)
+    n_cols = int(np.ceil(params.space_size[0] / params.voxel_size[0]))
+    cols = np.clip((st.position[:, 0] / params.voxel_size[0]).astype(np.int64), 0, n_cols - 1)
+    hist = np.bincount(cols, minlength=n_cols)
+    run = NativeSlabRunner(params, SphConstants(mode=mode), col_hist=hist, bounds=[0, n_cols], device=0,
+                           compact_every=2, migrant_frac=1.0 if mode == "PIPE" else 0.05, own_slack=2.0)
+    # shuffle the slot order: arrival order on a slab is arbitrary, only the global ids define the in-cell order
+    perm = np.random.default_rng(5).permutation(n)
+    run.load_global(st.position, st.velocity)
+    k = int(run.counters[0].item())
+    idx = torch.as_tensor(perm[:k], device=run.P.device)
+    run.P[:k], run.V[:k], run.G[:k] = run.P[:k][idx].clone(), run.V[:k][idx].clone(), run.G[:k][idx].clone()
+    snap = run.snapshot()
+    run.step(steps)
+    assert run.count_global() == n
+    pos, vel, rho = run.gather_global(n)
+    s = B200SPHStrategy(params, SphConstants(mode=mode))
+    s.upload(st)
+    s.step(steps)
+    ref = s.download()
+    eq = lambda a, b: bool(np.all((a == b) | (np.isnan(a) & np.isnan(b))))  # noqa: E731
+    assert eq(pos, ref.position) and eq(vel, ref.velocity) and eq(rho, ref.density)
+    if mode == "PIPE":   # the xoroshiro states travelled with the recycled particles
+        assert np.array_equal(run.R.cpu().numpy().view(np.uint64), s.rng_states())
+    # snapshot / restore (bench windows) incl. the RNG states: the same steps again give the same bits
+    run.restore(snap)
+    run.step(steps)
+    pos2, vel2, rho2 = run.gather_global(n)
+    assert eq(pos2, pos) and eq(vel2, vel) and eq(rho2, rho)
+    s.close()
+    run.close()
