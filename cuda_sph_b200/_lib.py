@@ -33,6 +33,15 @@ class SphStats(C.Structure):
                 ("steps_done", C.c_int64)]
 
 
+class SphFrameStats(C.Structure):
+    _fields_ = [("steps_done", C.c_int64), ("n_particles", C.c_int32), ("n_dead", C.c_int32),
+                ("n_nonfinite", C.c_int32), ("reserved", C.c_int32), ("max_position", C.c_float),
+                ("min_position", C.c_float), ("max_velocity", C.c_float), ("max_speed", C.c_float),
+                ("max_density", C.c_float), ("neighbour_hist", C.c_int32 * 33)]
+
+
+GEN_BOX_WALL, GEN_UNIFORM, GEN_PIPE = 0, 1, 2
+
 # every symbol include/sph_b200.h declares: name -> (restype, argtypes)
 _H = C.c_void_p
 _P = C.c_void_p
@@ -74,6 +83,12 @@ EXPORTS = {
     "sph_get_rng_states": (C.c_int, [_H, _P]),
     "sph_set_rng_states": (C.c_int, [_H, _P]),
     "sph_get_stats": (C.c_int, [_H, C.POINTER(SphStats)]),
+    "sph_export_begin": (C.c_int, [_H, C.c_int32, C.c_int32]),
+    "sph_export_wait": (C.c_int, [_H, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                  C.POINTER(C.c_int64)]),
+    "sph_generate_state": (C.c_int, [_H, C.c_int32, C.c_uint64]),
+    "sph_get_frame_stats": (C.c_int, [_H, C.POINTER(SphFrameStats)]),
+    "sph_export_stats": (C.c_int, [_H, C.c_int32, C.POINTER(SphFrameStats)]),
     "sph_n_cells": (C.c_int64, [_H]),
     "sph_cell_dims": (C.c_int, [_H, _P, _P]),
     "sph_device_ptr": (C.c_int, [_H, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),

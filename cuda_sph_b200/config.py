@@ -91,3 +91,53 @@ def start_state_inside_pipe(particle_count, pipe: Pipe, seed=0, dtype=np.float64
     pos = np.stack([x, table[0, 1] + r * np.cos(theta), table[0, 2] + r * np.sin(theta)], axis=1)
     pos = pos.astype(np.float32)
     return SimulationState(pos.astype(dtype), np.zeros((n, 3), dtype), np.zeros(n, dtype))
+
+
+# ---- host mirror of the device-side start-state generators (csrc/sph_kernels.cuh: generate_kernel) ------------------
+def _u24(seed: int, ids: np.ndarray, stream: int) -> np.ndarray:
+    """Draw `stream` of every particle: SplitMix64 finaliser of seed + golden * (16 id + stream + 1), top 24 bits."""
+    with np.errstate(over="ignore"):
+        z = np.uint64(seed) + np.uint64(0x9E3779B97F4A7C15) * (ids.astype(np.uint64) * np.uint64(16)
+                                                                + np.uint64(stream + 1))
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z ^= z >> np.uint64(31)
+    return (z >> np.uint64(40)).astype(np.float32) * np.float32(2.0 ** -24)
+
+
+def hashed_start_state(kind: str, params: SimulationParameters, seed: int = 0) -> SimulationState:
+    """The state sph_generate_state(kind, seed) writes on the device, bit for bit (section 8(f)2): a pure function of
+    (kind, seed, particle id), so any rank of a multi-GPU run can produce its own particles."""
+    n = int(params.particle_count)
+    ids = np.arange(n, dtype=np.uint64)
+    space = np.asarray(params.space_size, np.float64)
+    if kind in ("box_wall", "uniform"):
+        ext = space.copy()
+        if kind == "box_wall":
+            ext[0] = space[0] * 0.1
+        ext32 = ext.astype(np.float32)
+        top = np.nextafter(space.astype(np.float32), np.float32(0))
+        pos = np.stack([np.minimum(_u24(seed, ids, d) * ext32[d], top[d]) for d in range(3)], axis=1)
+        base = np.asarray([1.5, -5.0, -5.0], np.float32)
+        vel = np.stack([(_u24(seed, ids, 3 + d) + np.float32(-0.5)) + base[d] for d in range(3)], axis=1)
+        return SimulationState(pos.astype(np.float64), vel.astype(np.float64), np.zeros(n))
+    if kind != "pipe":
+        raise ValueError(kind)
+    t = np.ascontiguousarray(params.pipe.to_numpy(), np.float64)
+    rows = len(t)
+    length = t[rows - 1, 0] - t[0, 0]
+    xd = _u24(seed, ids, 0).astype(np.float64) * length
+    starts = t[1:rows - 1, 0] - t[0, 0]                       # a particle is in segment s while x < start of s + 1
+    s_ = np.searchsorted(starts, xd, side="right")
+    r0, r1 = t[s_, 3], t[s_ + 1, 3]
+    frac = (xd - (t[s_, 0] - t[0, 0])) / t[s_, 4]
+    rmax = (r0 + (r1 - r0) * frac) * 0.98
+    a, b, done = np.zeros(n), np.zeros(n), np.zeros(n, bool)
+    for tr in range(7):
+        ta = _u24(seed, ids, 1 + 2 * tr).astype(np.float64) * 2.0 - 1.0
+        tb = _u24(seed, ids, 2 + 2 * tr).astype(np.float64) * 2.0 - 1.0
+        ok = ~done & (ta * ta + tb * tb <= 1.0)
+        a[ok], b[ok] = ta[ok], tb[ok]
+        done |= ok
+    pos = np.stack([xd + t[0, 0], t[0, 1] + a * rmax, t[0, 2] + b * rmax], axis=1).astype(np.float32)
+    return SimulationState(pos.astype(np.float64), np.zeros((n, 3)), np.zeros(n))

@@ -91,6 +91,13 @@ struct SphEngine {
     void *stage = nullptr;
     size_t stage_bytes = 0;
     uint32_t *stats_d = nullptr;
+    // frame export (sph_export_begin / sph_export_wait): device staging + pinned host buffer per slot
+    double *exp_dev[3]{}, *exp_host[3]{};
+    int64_t exp_cap[3]{}, exp_n[3]{};
+    cudaEvent_t exp_ev[3]{}, exp_packed = nullptr;
+    uint32_t *exp_stats_dev[3]{}, *exp_stats_host[3]{};   // frame statistics of the exported frame (40 words + dead range)
+    int64_t exp_steps[3]{};
+    uint32_t *fstats_d = nullptr;
     // snapshot (sph_save_state)
     float4 *snap_pos = nullptr, *snap_vel = nullptr;
     uint64_t *snap_rng = nullptr;
@@ -388,6 +395,15 @@ int sph_destroy(sph_handle_t e) {
         if (q) cudaFree(q);
     for (auto &ev : e->ev)
         if (ev) cudaEventDestroy(ev);
+    for (int k = 0; k < 3; ++k) {
+        if (e->exp_dev[k]) cudaFree(e->exp_dev[k]);
+        if (e->exp_host[k]) cudaFreeHost(e->exp_host[k]);
+        if (e->exp_ev[k]) cudaEventDestroy(e->exp_ev[k]);
+        if (e->exp_stats_dev[k]) cudaFree(e->exp_stats_dev[k]);
+        if (e->exp_stats_host[k]) cudaFreeHost(e->exp_stats_host[k]);
+    }
+    if (e->exp_packed) cudaEventDestroy(e->exp_packed);
+    if (e->fstats_d) cudaFree(e->fstats_d);
     if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     if (e->aux_stream) cudaStreamDestroy(e->aux_stream);
@@ -690,6 +706,13 @@ int sph_step_timed(sph_handle_t e, int32_t n_steps, SphTimings *t) {
     return 0;
 }
 
+static int ensure_copy_stream(SphEngine *e) {
+    if (e->copy_stream) return 0;
+    CK(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+    for (auto &ev : e->ev_copy) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    return 0;
+}
+
 // The reference-facing call.  Same result as sph_upload + sph_step(1) + sph_download, but the host copies are
 // interleaved with the step on two streams: everything up to and including the density sweep needs positions only and
 // runs while the velocities are still on their way in, and the density goes out while the force sweep runs (the copies are PCIe-bound: 104 B per particle against a 0.7 us step).
@@ -702,12 +725,7 @@ int sph_compute_next_state(sph_handle_t e, const double *pos_in, const double *v
     CK(cudaSetDevice(e->device));
     const size_t n = e->n, vec = 3 * n * sizeof(double);
     if (ensure_stage(e, 7 * n * sizeof(double))) return 1;
-    if (!e->copy_stream) {
-        CK(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
-        CK(cudaEventCreateWithFlags(&e->ev_copy[0], cudaEventDisableTiming));
-        CK(cudaEventCreateWithFlags(&e->ev_copy[1], cudaEventDisableTiming));
-        CK(cudaEventCreateWithFlags(&e->ev_copy[2], cudaEventDisableTiming));
-    }
+    if (ensure_copy_stream(e)) return 1;
     cudaStream_t s = e->stream, c2 = e->copy_stream;
     double *dpos = (double *)e->stage, *dvel = dpos + 3 * n, *drho = dvel + 3 * n;
     const int g256 = (e->n + 255) / 256;
@@ -740,6 +758,138 @@ int sph_compute_next_state(sph_handle_t e, const double *pos_in, const double *v
     e->has_state = true;
     e->steps_done += 1;
     e->launches += e->launches_per_step + 5;   // + 2 packs, velocity gather, density unsort, unpack
+    return 0;
+}
+
+int sph_export_begin(sph_handle_t e, int32_t slot, int32_t stride) {
+    if (!e) return fail("null handle");
+    if (slot < 0 || slot > 2) return fail("export slot must be 0, 1 or 2");
+    if (stride < 1) return fail("stride must be >= 1");
+    if (e->slab) return fail("frame export works on single-GPU handles");
+    if (!e->has_state) return fail("no particle state");
+    CK(cudaSetDevice(e->device));
+    if (ensure_copy_stream(e)) return 1;
+    const int64_t n_out = ((int64_t)e->n + stride - 1) / stride;
+    if (!e->exp_ev[slot]) CK(cudaEventCreateWithFlags(&e->exp_ev[slot], cudaEventDisableTiming));
+    if (!e->exp_packed) CK(cudaEventCreateWithFlags(&e->exp_packed, cudaEventDisableTiming));
+    if (e->exp_cap[slot] < n_out) {
+        CK(cudaEventSynchronize(e->exp_ev[slot]));
+        if (e->exp_dev[slot]) cudaFree(e->exp_dev[slot]);
+        if (e->exp_host[slot]) cudaFreeHost(e->exp_host[slot]);
+        e->exp_dev[slot] = e->exp_host[slot] = nullptr;
+        e->exp_cap[slot] = 0;
+        CK(cudaMalloc((void **)&e->exp_dev[slot], 7 * sizeof(double) * (size_t)n_out));
+        CK(cudaHostAlloc((void **)&e->exp_host[slot], 7 * sizeof(double) * (size_t)n_out, cudaHostAllocDefault));
+        e->exp_cap[slot] = n_out;
+    }
+    // the slot's previous copy must have left the device staging buffer before it is overwritten
+    CK(cudaStreamWaitEvent(e->stream, e->exp_ev[slot], 0));
+    export_pack_kernel<<<(int)((n_out + 255) / 256), 256, 0, e->stream>>>(e->pos_m, e->vel_m, e->exp_dev[slot],
+                                                                        (int)n_out, stride);
+    CK(cudaGetLastError());
+    // the frame's statistics ride along (section 8(f)4): reduced on the main stream right after the frame's steps
+    if (!e->exp_stats_dev[slot]) {
+        CK(cudaMalloc((void **)&e->exp_stats_dev[slot], 42 * sizeof(uint32_t)));
+        CK(cudaHostAlloc((void **)&e->exp_stats_host[slot], 42 * sizeof(uint32_t), cudaHostAllocDefault));
+    }
+    frame_stats_init_kernel<<<1, 64, 0, e->stream>>>(e->exp_stats_dev[slot], e->cell_range + e->grid.ncells,
+                                                     e->steps_done > 0 ? 1 : 0);
+    frame_stats_kernel<<<(e->n + 255) / 256, 256, 0, e->stream>>>(e->pos_m, e->vel_m, e->ncnt, e->n,
+                                                                  e->steps_done > 0 ? 1 : 0, e->exp_stats_dev[slot]);
+    CK(cudaGetLastError());
+    e->exp_steps[slot] = e->steps_done;
+    CK(cudaEventRecord(e->exp_packed, e->stream));
+    CK(cudaStreamWaitEvent(e->copy_stream, e->exp_packed, 0));
+    CK(cudaMemcpyAsync(e->exp_host[slot], e->exp_dev[slot], 7 * sizeof(double) * (size_t)n_out, cudaMemcpyDeviceToHost,
+                       e->copy_stream));
+    CK(cudaMemcpyAsync(e->exp_stats_host[slot], e->exp_stats_dev[slot], 42 * sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                       e->copy_stream));
+    CK(cudaEventRecord(e->exp_ev[slot], e->copy_stream));
+    e->exp_n[slot] = n_out;
+    e->launches += 3;
+    return 0;
+}
+
+int sph_export_wait(sph_handle_t e, int32_t slot, double **pos, double **vel, double **rho, int64_t *n_out) {
+    if (!e) return fail("null handle");
+    if (slot < 0 || slot > 2 || !e->exp_ev[slot] || e->exp_n[slot] == 0) return fail("no export in flight on this slot");
+    CK(cudaSetDevice(e->device));
+    CK(cudaEventSynchronize(e->exp_ev[slot]));
+    const size_t m = (size_t)e->exp_n[slot];
+    if (pos) *pos = e->exp_host[slot];
+    if (vel) *vel = e->exp_host[slot] + 3 * m;
+    if (rho) *rho = e->exp_host[slot] + 6 * m;
+    if (n_out) *n_out = (int64_t)m;
+    return 0;
+}
+
+int sph_generate_state(sph_handle_t e, int32_t kind, uint64_t seed) {
+    if (!e) return fail("null handle");
+    if (e->slab) return fail("start-state generators work on single-GPU handles");
+    if (kind < 0 || kind > 2) return fail("unknown generator kind");
+    if (kind == SPH_GEN_PIPE && !e->pipe_d) return fail("the pipe generator needs sph_set_pipe");
+    CK(cudaSetDevice(e->device));
+    GenArgs ga{};
+    ga.kind = kind;
+    ga.seed = seed;
+    for (int d = 0; d < 3; ++d) {
+        const double full = e->p.space_size[d];
+        ga.ext[d] = (float)((kind == SPH_GEN_BOX_WALL && d == 0) ? full * 0.1 : full);
+        ga.top[d] = std::nextafter((float)full, 0.f);
+    }
+    ga.pipe = e->pipe_d;
+    ga.pipe_rows = e->pipe_rows;
+    generate_kernel<<<(e->n + 255) / 256, 256, 0, e->stream>>>(e->pos_m, e->vel_m, e->n, ga);
+    CK(cudaGetLastError());
+    e->launches += 1;
+    e->has_state = true;
+    return 0;
+}
+
+static void decode_frame_stats(const SphEngine *e, const uint32_t *h, int64_t steps, SphFrameStats *st) {
+    auto unord = [](uint32_t u) {
+        u = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+        float f;
+        memcpy(&f, &u, 4);
+        return f;
+    };
+    memset(st, 0, sizeof(*st));
+    st->steps_done = steps;
+    st->n_particles = e->n;
+    st->n_dead = (int32_t)h[41] - (int32_t)h[40];
+    st->n_nonfinite = (int32_t)h[0];
+    const bool any = h[1] != 0;   // at least one finite particle
+    st->max_position = any ? unord(h[1]) : NAN;
+    st->min_position = any ? unord(h[2]) : NAN;
+    st->max_velocity = any ? unord(h[3]) : NAN;
+    st->max_speed = any ? unord(h[4]) : NAN;
+    st->max_density = h[5] ? unord(h[5]) : NAN;
+    for (int k = 0; k < 33; ++k) st->neighbour_hist[k] = (int32_t)h[6 + k];
+}
+
+int sph_export_stats(sph_handle_t e, int32_t slot, SphFrameStats *st) {
+    if (!e || !st) return fail("null argument");
+    if (slot < 0 || slot > 2 || !e->exp_ev[slot] || e->exp_n[slot] == 0) return fail("no export in flight on this slot");
+    CK(cudaSetDevice(e->device));
+    CK(cudaEventSynchronize(e->exp_ev[slot]));
+    decode_frame_stats(e, e->exp_stats_host[slot], e->exp_steps[slot], st);
+    return 0;
+}
+
+int sph_get_frame_stats(sph_handle_t e, SphFrameStats *st) {
+    if (!e || !st) return fail("null argument");
+    if (e->slab) return fail("frame statistics work on single-GPU handles");
+    CK(cudaSetDevice(e->device));
+    if (!e->fstats_d) CK(cudaMalloc((void **)&e->fstats_d, 42 * sizeof(uint32_t)));
+    frame_stats_init_kernel<<<1, 64, 0, e->stream>>>(e->fstats_d, e->cell_range + e->grid.ncells, e->steps_done > 0 ? 1 : 0);
+    frame_stats_kernel<<<(e->n + 255) / 256, 256, 0, e->stream>>>(e->pos_m, e->vel_m, e->ncnt, e->n,
+                                                                  e->steps_done > 0 ? 1 : 0, e->fstats_d);
+    CK(cudaGetLastError());
+    uint32_t h[42];
+    CK(cudaMemcpyAsync(h, e->fstats_d, sizeof(h), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    decode_frame_stats(e, h, e->steps_done, st);
+    e->launches += 2;
     return 0;
 }
 

@@ -205,4 +205,140 @@ stats_kernel(const float4 *__restrict__ pos_m, const float4 *__restrict__ vel_m,
     }
 }
 
+// ---- frame export: fp64, id order, every stride-th particle (section 8(f)1) -----------------------------------------
+__global__ void __launch_bounds__(256)
+export_pack_kernel(const float4 *__restrict__ pos_m, const float4 *__restrict__ vel_m, double *__restrict__ out, int n_out,
+                   int stride) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_out) return;
+    const size_t i = (size_t)k * stride;
+    const float4 p = pos_m[i], v = vel_m[i];
+    double *pos3 = out, *vel3 = out + 3 * (size_t)n_out, *rho = out + 6 * (size_t)n_out;
+    pos3[3 * (size_t)k] = p.x;
+    pos3[3 * (size_t)k + 1] = p.y;
+    pos3[3 * (size_t)k + 2] = p.z;
+    vel3[3 * (size_t)k] = v.x;
+    vel3[3 * (size_t)k + 1] = v.y;
+    vel3[3 * (size_t)k + 2] = v.z;
+    rho[k] = p.w;
+}
+
+// ---- seeded start states (section 8(f)2): counter-based draws, mirrored bit for bit by cuda_sph_b200/config.py -------
+// draw `stream` of particle `id`: SplitMix64 finaliser of seed + golden * (16 id + stream + 1), top 24 bits -> [0, 1)
+__host__ __device__ inline float gen_u24(uint64_t seed, uint64_t id, uint32_t stream) {
+    uint64_t z = seed + 0x9E3779B97F4A7C15ULL * (id * 16ULL + stream + 1ULL);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    z ^= z >> 31;
+    return (float)(uint32_t)(z >> 40) * 5.9604644775390625e-08f;   // exact: 24 bits * 2^-24
+}
+
+struct GenArgs {
+    int32_t kind;
+    uint64_t seed;
+    float ext[3];        // box kinds: extent of the filled region per dimension (fp32)
+    float top[3];        // largest fp32 below the space size (positions stay inside the domain)
+    const double *pipe;  // pipe kind: rows x 5 table
+    int32_t pipe_rows;
+};
+
+__global__ void __launch_bounds__(256)
+generate_kernel(float4 *__restrict__ pos_m, float4 *__restrict__ vel_m, int n, GenArgs ga) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float x, y, z, vx = 0.f, vy = 0.f, vz = 0.f;
+    if (ga.kind != 2) {
+        x = fminf(__fmul_rn(gen_u24(ga.seed, i, 0), ga.ext[0]), ga.top[0]);
+        y = fminf(__fmul_rn(gen_u24(ga.seed, i, 1), ga.ext[1]), ga.top[1]);
+        z = fminf(__fmul_rn(gen_u24(ga.seed, i, 2), ga.ext[2]), ga.top[2]);
+        vx = __fadd_rn(__fadd_rn(gen_u24(ga.seed, i, 3), -0.5f), 1.5f);
+        vy = __fadd_rn(__fadd_rn(gen_u24(ga.seed, i, 4), -0.5f), -5.0f);
+        vz = __fadd_rn(__fadd_rn(gen_u24(ga.seed, i, 5), -0.5f), -5.0f);
+    } else {
+        // config.py:105-115: x uniform along the pipe; (y, z) uniform over 98 % of the local disc.  fp64 with explicit
+        // roundings (no transcendental functions: the disc is sampled by rejection from the draw sequence)
+        const int rows = ga.pipe_rows;
+        const double len = ga.pipe[5 * (rows - 1)] - ga.pipe[0];
+        const double xd = __dmul_rn((double)gen_u24(ga.seed, i, 0), len);
+        int s = 0;
+        while (s + 2 < rows && xd >= ga.pipe[5 * (s + 1)] - ga.pipe[0]) ++s;
+        const double r0 = ga.pipe[5 * s + 3], r1 = ga.pipe[5 * (s + 1) + 3];
+        const double frac = __ddiv_rn(__dsub_rn(xd, ga.pipe[5 * s] - ga.pipe[0]), ga.pipe[5 * s + 4]);
+        const double rmax = __dmul_rn(__dadd_rn(r0, __dmul_rn(__dsub_rn(r1, r0), frac)), 0.98);
+        double a = 0.0, b = 0.0;
+        for (int tr = 0; tr < 7; ++tr) {
+            const double ta = __dsub_rn(__dmul_rn((double)gen_u24(ga.seed, i, 1 + 2 * tr), 2.0), 1.0);
+            const double tb = __dsub_rn(__dmul_rn((double)gen_u24(ga.seed, i, 2 + 2 * tr), 2.0), 1.0);
+            if (__dadd_rn(__dmul_rn(ta, ta), __dmul_rn(tb, tb)) <= 1.0) {
+                a = ta;
+                b = tb;
+                break;
+            }
+        }
+        x = (float)__dadd_rn(xd, ga.pipe[0]);
+        y = (float)__dadd_rn(ga.pipe[1], __dmul_rn(a, rmax));
+        z = (float)__dadd_rn(ga.pipe[2], __dmul_rn(b, rmax));
+    }
+    pos_m[i] = make_float4(x, y, z, 0.f);
+    vel_m[i] = make_float4(vx, vy, vz, 0.f);
+}
+
+// ---- per-frame reductions (section 8(f)4; analize.py:9-14) ----------------------------------------------------------
+// out: [0] non-finite particles, [1] max position bits (ordered-int encoding), [2] min position, [3] max velocity
+// component, [4] max speed, [5] max density, [6..38] neighbour-count histogram
+__device__ __forceinline__ uint32_t ord_f32(float f) {   // monotone float -> uint mapping
+    const uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+// out[0..39] as above, out[40..41] = the dead cell's range at this moment (begin, end)
+__global__ void frame_stats_init_kernel(uint32_t *__restrict__ out, const int2 *__restrict__ dead_range, int have_range) {
+    const int k = threadIdx.x;
+    if (k < 40) out[k] = (k == 2) ? 0xffffffffu : 0u;
+    if (k == 40) out[40] = have_range ? (uint32_t)dead_range->x : 0u;
+    if (k == 41) out[41] = have_range ? (uint32_t)dead_range->y : 0u;
+}
+
+__global__ void __launch_bounds__(256)
+frame_stats_kernel(const float4 *__restrict__ pos_m, const float4 *__restrict__ vel_m, const uint8_t *__restrict__ ncnt,
+                   int n, int have_counts, uint32_t *__restrict__ out) {
+    __shared__ uint32_t hist[33];
+    if (threadIdx.x < 33) hist[threadIdx.x] = 0;
+    __syncthreads();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t bad = 0, pmax = 0, pmin = 0xffffffffu, vmax = 0, smax = 0, dmax = 0;
+    if (i < n) {
+        const float4 p = pos_m[i], v = vel_m[i];
+        const bool fin = isfinite(p.x) && isfinite(p.y) && isfinite(p.z) && isfinite(v.x) && isfinite(v.y) &&
+                         isfinite(v.z);
+        bad = fin ? 0u : 1u;
+        if (fin) {
+            pmax = ord_f32(fmaxf(p.x, fmaxf(p.y, p.z)));
+            pmin = ord_f32(fminf(p.x, fminf(p.y, p.z)));
+            vmax = ord_f32(fmaxf(v.x, fmaxf(v.y, v.z)));
+            smax = ord_f32(sqrtf(v.x * v.x + v.y * v.y + v.z * v.z));
+        }
+        if (isfinite(p.w)) dmax = ord_f32(p.w);
+        if (have_counts) atomicAdd(&hist[min((int)(ncnt[i] & 0x7f), 32)], 1u);   // ncnt is in sorted order: a histogram does not care
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        bad += __shfl_xor_sync(0xffffffffu, bad, o);
+        pmax = max(pmax, __shfl_xor_sync(0xffffffffu, pmax, o));
+        pmin = min(pmin, __shfl_xor_sync(0xffffffffu, pmin, o));
+        vmax = max(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+        smax = max(smax, __shfl_xor_sync(0xffffffffu, smax, o));
+        dmax = max(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (bad) atomicAdd(&out[0], bad);
+        atomicMax(&out[1], pmax);
+        atomicMin(&out[2], pmin);
+        atomicMax(&out[3], vmax);
+        atomicMax(&out[4], smax);
+        atomicMax(&out[5], dmax);
+    }
+    __syncthreads();
+    if (threadIdx.x < 33 && hist[threadIdx.x]) atomicAdd(&out[6 + threadIdx.x], hist[threadIdx.x]);
+}
+
 }  // namespace sph

@@ -154,6 +154,49 @@ class B200SPHStrategy:
         self.new_state = SimulationState(pos, vel, rho)
         return self.new_state
 
+    # ------------------------------------------------------------------ frame export pipeline (section 8(f)1)
+    def export_async(self, slot: int, stride: int = 1) -> None:
+        """Snapshot the state (fp64, id order, every `stride`-th particle) into pinned host buffer `slot` (0..2) on a
+        second stream; returns at once -- the copy runs under the steps enqueued next."""
+        _lib.check(self._lib.sph_export_begin(self._h, int(slot), int(stride)))
+
+    def export_wait(self, slot: int, copy: bool = True) -> SimulationState:
+        """The frame of `slot` once its copy has landed.  copy=False returns views of the pinned buffer, valid until the
+        slot is exported into again."""
+        p, v, r, m = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_int64()
+        _lib.check(self._lib.sph_export_wait(self._h, int(slot), C.byref(p), C.byref(v), C.byref(r), C.byref(m)))
+        k = int(m.value)
+
+        def view(ptr, shape):
+            buf = (C.c_double * int(np.prod(shape))).from_address(ptr.value)
+            a = np.frombuffer(buf, dtype=np.float64).reshape(shape)
+            return a.copy() if copy else a
+        return SimulationState(view(p, (k, 3)), view(v, (k, 3)), view(r, (k,)))
+
+    def generate_state(self, kind: str, seed: int = 0) -> None:
+        """Seeded start state generated on the device (section 8(f)2; config.hashed_start_state is the host mirror):
+        kind = 'box_wall' (config.py:84-95), 'uniform', 'pipe' (config.py:105-115)."""
+        code = {"box_wall": _lib.GEN_BOX_WALL, "uniform": _lib.GEN_UNIFORM, "pipe": _lib.GEN_PIPE}[kind]
+        _lib.check(self._lib.sph_generate_state(self._h, code, C.c_uint64(int(seed))))
+
+    @staticmethod
+    def _stats_dict(st) -> dict:
+        out = {name: getattr(st, name) for name, _ in st._fields_ if name not in ("neighbour_hist", "reserved")}
+        out["neighbour_hist"] = [int(x) for x in st.neighbour_hist]
+        return out
+
+    def frame_stats(self) -> dict:
+        """On-device reductions over the current state (analize.py:9-14 + neighbour-count histogram)."""
+        st = _lib.SphFrameStats()
+        _lib.check(self._lib.sph_get_frame_stats(self._h, C.byref(st)))
+        return self._stats_dict(st)
+
+    def export_stats(self, slot: int) -> dict:
+        """The same reductions for the frame exported into `slot` (they travelled with it)."""
+        st = _lib.SphFrameStats()
+        _lib.check(self._lib.sph_export_stats(self._h, int(slot), C.byref(st)))
+        return self._stats_dict(st)
+
     def save_state(self):
         """Device-side snapshot of the particle state (checkpoint)."""
         _lib.check(self._lib.sph_save_state(self._h))

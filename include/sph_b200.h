@@ -172,6 +172,45 @@ int sph_get_stats(sph_handle_t h, SphStats *stats);
 int64_t sph_n_cells(sph_handle_t h);
 int sph_cell_dims(sph_handle_t h, int32_t *ceil3, int32_t *trunc3);
 
+/* ---- frame export pipeline (section 8(f)1).  Replaces the per-frame __finalize_computation + np.save sequence of
+ * state_generator.py:26-37 / saver.py:28-36 for device-resident runs.  sph_export_begin snapshots the state (fp64,
+ * particle-id order, every `stride`-th id: stride > 1 down-samples, e.g. for the viewer's 100 000-point cap,
+ * gl_point_field.py:11) into one of three engine-owned PINNED host buffers on a second stream and returns at once, so
+ * the copy runs under the next steps; sph_export_wait blocks until that buffer is complete and returns pointers into
+ * it (valid until the slot is used again): position (n_out,3), velocity (n_out,3), density (n_out). */
+int sph_export_begin(sph_handle_t h, int32_t slot, int32_t stride);
+int sph_export_wait(sph_handle_t h, int32_t slot, double **position, double **velocity, double **density,
+                    int64_t *n_out);
+
+/* ---- seeded start states generated ON THE DEVICE (section 8(f)2).  Replaces the per-particle Python loops with
+ * unseeded `random` of config.py:79-120.  kind: 0 = dam-break column (first 10 % of x, velocity [1.5,-5,-5] +- 0.5,
+ * config.py:84-95), 1 = uniform box (same velocities), 2 = inside the pipe (uniform in x, uniform over 98 % of the
+ * local disc, zero velocity, config.py:105-115; needs sph_set_pipe).  Counter-based (SplitMix64 of seed, particle id
+ * and draw index), so the state is a pure function of (kind, seed, id) and cuda_sph_b200/config.py mirrors it on the
+ * host bit for bit. */
+#define SPH_GEN_BOX_WALL 0
+#define SPH_GEN_UNIFORM 1
+#define SPH_GEN_PIPE 2
+int sph_generate_state(sph_handle_t h, int32_t kind, uint64_t seed);
+
+/* ---- per-frame reductions on the device (section 8(f)4; analize.py:9-14 prints max position / velocity / density per
+ * epoch, np.max over all components).  Maxima are over finite values; non-finite particles are counted. */
+typedef struct SphFrameStats {
+    int64_t steps_done;
+    int32_t n_particles;
+    int32_t n_dead;              /* particles in the dead cell at the most recent step       */
+    int32_t n_nonfinite;         /* particles with a non-finite position or velocity component              */
+    int32_t reserved;
+    float max_position;          /* np.max(position)  analize.py:12 */
+    float min_position;
+    float max_velocity;          /* np.max(velocity)  analize.py:13 */
+    float max_speed;
+    float max_density;           /* np.max(density)   analize.py:14 */
+    int32_t neighbour_hist[33];  /* particles by neighbour count (0..32, self included) of the most recent step */
+} SphFrameStats;
+int sph_get_frame_stats(sph_handle_t h, SphFrameStats *stats);               /* current state; synchronises */
+int sph_export_stats(sph_handle_t h, int32_t slot, SphFrameStats *stats);    /* of the frame exported into `slot` */
+
 /* Device pointers for zero-copy wrapping (torch / __cuda_array_interface__).  which: 0 = master position float4[N]
  * (x,y,z,density), 1 = master velocity float4[N], 2 = sorted ids int32[N], 3 = sorted position float4[N],
  * 4 = global ids int32[capacity] (x-slab mode), 5 = xoroshiro states uint64[2 * count] (PIPE mode),
