@@ -18,6 +18,7 @@
 #include "slab_exchange.cuh"
 #include "sph_kernels.cuh"
 #include "sweep.cuh"
+#include "sweep_dense.cuh"
 #include "sweep_flat.cuh"
 #include "sweep_rows.cuh"
 
@@ -53,6 +54,7 @@ struct SphEngine {
     float4 *spress = nullptr, *svisc = nullptr;
     float *srho = nullptr;
     uint16_t *nlist = nullptr;   // [n][32] neighbour lists (virtual-list indices), density -> force
+    uint32_t *dlist = nullptr;   // [n][32] neighbour lists of the dense tiles (sorted indices; sweep_dense.cuh)
     uint8_t *ncnt = nullptr;     // [n] neighbour counts
     // keys / sort buffers
     uint32_t *keys = nullptr, *ka = nullptr, *va = nullptr, *kb = nullptr, *vb = nullptr;
@@ -315,6 +317,7 @@ int sph_create(const SphParams *params, int device, sph_handle_t *out) {
     if (e->slab) ALLOC(e->gid, n);
     ALLOC(e->stats_d, 4);
     ALLOC(e->nlist, (size_t)n * 32);
+    ALLOC(e->dlist, (size_t)n * 32);
     ALLOC(e->ncnt, n);
     if (params->flags & SPH_FLAG_RECORD_TERMS) {
         ALLOC(e->spress, n);
@@ -362,6 +365,7 @@ int sph_create(const SphParams *params, int device, sph_handle_t *out) {
     for (auto &ev : e->ev) cudaEventCreate(&ev);
     cudaFuncSetAttribute(density_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DensityRowsSmem));
     cudaFuncSetAttribute(density_flat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FlatSmem));
+    cudaFuncSetAttribute(density_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DenseSmem));
     cudaFuncSetAttribute(density_rows_items_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)sizeof(DensityRowsSmem));
     cudaFuncSetAttribute(force_rows_items_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -387,7 +391,7 @@ int sph_destroy(sph_handle_t e) {
     cudaSetDevice(e->device);
     cudaDeviceSynchronize();
     invalidate_graph(e);
-    void *ptrs[] = {e->pos_m, e->vel_m, e->spos, e->svel, e->sforce, e->spress, e->svisc, e->srho, e->nlist, e->ncnt,
+    void *ptrs[] = {e->pos_m, e->vel_m, e->spos, e->svel, e->sforce, e->spress, e->svisc, e->srho, e->nlist, e->dlist, e->ncnt,
                     e->keys, e->ka, e->va, e->kb, e->vb, e->block_hist, e->digit_total, e->os_ctrl, e->tile_plans, e->refused, e->cell_range, e->pipe_d,
                     e->rng, e->gid, e->stage, e->stats_d, e->snap_pos, e->snap_vel, e->snap_rng, e->sendbuf, e->recvbuf,
                     e->slab_counters, e->tmp_gid};
@@ -595,13 +599,16 @@ static int enqueue_step(SphEngine *e, bool timed, int n, int n_own, int stages =
         cudaStream_t x = e->aux_stream;
         int *list_b = e->refused + 2 + 4 * (size_t)e->ntiles_rb;
         if (stages & 2) {
-            rows_plan_kernel<<<(grb + RP_WARPS - 1) / RP_WARPS, RP_WARPS * 32, 0, s>>>(sa, e->grid, e->tile_plans, grb,
-                                                                                       e->refused, e->refused + 2);
-            // fork: the passes of tiles whose rows do not fit run next to the main density sweep
+            rows_plan_kernel<<<(grb + RP_WARPS - 1) / RP_WARPS, RP_WARPS * 32, 0, s>>>(
+                sa, e->grid, e->tile_plans, grb, e->refused, e->refused + 2, e->flat_density ? 1 : 0);
+            // fork: the tiles whose rows do not fit run next to the main density sweep
             cudaEventRecord(e->ev_fork[0], s);
             cudaStreamWaitEvent(x, e->ev_fork[0], 0);
-            density_rows_items_kernel<<<ITEM_CTAS, RB_THREADS, sizeof(DensityRowsSmem), x>>>(sa, e->grid, e->consts,
-                                                                                             sa.n_items, sa.items);
+            if (e->flat_density)
+                density_dense_kernel<<<148 * 3, DN_THREADS, sizeof(DenseSmem), x>>>(sa, e->grid, e->consts, e->dlist);
+            else
+                density_rows_items_kernel<<<ITEM_CTAS, RB_THREADS, sizeof(DensityRowsSmem), x>>>(sa, e->grid, e->consts,
+                                                                                                 sa.n_items, sa.items);
             cudaEventRecord(e->ev_join[0], x);
             if (e->flat_density) {
                 const FlatArgs fa{list_b, e->refused + 1};
@@ -618,11 +625,17 @@ static int enqueue_step(SphEngine *e, bool timed, int n, int n_own, int stages =
             cudaEventRecord(e->ev_fork[1], s);
             cudaStreamWaitEvent(x, e->ev_fork[1], 0);
             if (e->spress) {
-                force_rows_items_kernel<true><<<ITEM_CTAS, RB_THREADS, sizeof(ForceRowsSmem), x>>>(sa, e->grid, e->consts);
+                if (e->flat_density)
+                    force_gather_kernel<true><<<148 * 8, RB_THREADS, 0, x>>>(sa, e->grid, e->consts, e->dlist);
+                else
+                    force_rows_items_kernel<true><<<ITEM_CTAS, RB_THREADS, sizeof(ForceRowsSmem), x>>>(sa, e->grid, e->consts);
                 cudaEventRecord(e->ev_join[1], x);
                 force_rows_kernel<true><<<grb, RB_THREADS, sizeof(ForceRowsSmem), s>>>(sa, e->grid, e->consts);
             } else {
-                force_rows_items_kernel<false><<<ITEM_CTAS, RB_THREADS, sizeof(ForceRowsSmem), x>>>(sa, e->grid, e->consts);
+                if (e->flat_density)
+                    force_gather_kernel<false><<<148 * 8, RB_THREADS, 0, x>>>(sa, e->grid, e->consts, e->dlist);
+                else
+                    force_rows_items_kernel<false><<<ITEM_CTAS, RB_THREADS, sizeof(ForceRowsSmem), x>>>(sa, e->grid, e->consts);
                 cudaEventRecord(e->ev_join[1], x);
                 force_rows_kernel<false><<<grb, RB_THREADS, sizeof(ForceRowsSmem), s>>>(sa, e->grid, e->consts);
             }
@@ -1183,7 +1196,8 @@ int sph_get_neighbour_lists(sph_handle_t e, int32_t *lists) {
     const size_t bytes = sizeof(int32_t) * (size_t)e->n * kMaxNeighbours;
     if (ensure_stage(e, std::max(bytes, 7 * sizeof(double) * (size_t)e->n))) return 1;
     const SweepArgs sa = sweep_args(e, e->sids, e->n, e->n);
-    neighbour_lists_kernel<<<(e->n + 127) / 128, 128, 0, e->stream>>>(sa, e->grid, e->consts, (int32_t *)e->stage);
+    neighbour_lists_kernel<<<(e->n + 127) / 128, 128, 0, e->stream>>>(sa, e->grid, e->consts, (int32_t *)e->stage,
+                                                                      e->flat_density ? e->dlist : nullptr);
     CK(cudaGetLastError());
     return d2h(e, lists, e->stage, bytes);
 }

@@ -233,7 +233,7 @@ constexpr int ITEM_CTAS = 148 * 2;   // grid of the work-item kernels
 
 __global__ void __launch_bounds__(RP_WARPS * 32)
 rows_plan_kernel(const SweepArgs a, const GridDesc g, TilePlan *__restrict__ plans, int ntiles,
-                 int *__restrict__ n_items, int *__restrict__ items) {
+                 int *__restrict__ n_items, int *__restrict__ items, int whole_tile_items) {
     const int lane = threadIdx.x & 31;
     const int tile = blockIdx.x * RP_WARPS + (threadIdx.x >> 5);
     if (tile >= ntiles) return;
@@ -288,12 +288,13 @@ rows_plan_kernel(const SweepArgs a, const GridDesc g, TilePlan *__restrict__ pla
         const bool fits = sum <= RB_CAP && ncell <= RB_MAXC;
         tp.fits = fits ? 1 : 0;
         if (!fits && g.aligned) {
-            // rows that do not fit shared memory: both sweeps take the tile as 32-particle passes.  The passes become
-            // work items (tile * 8 + 1 + pass) that the first CTAs of the sweeps run before their own tile, so the
-            // long items start first and run side by side instead of one after the other inside one CTA.
-            const int np = (min(RB_THREADS, a.n - p0) + 31) / 32;
+            // rows that do not fit the sweeps' shared-memory staging: the tile becomes a work item of the dense kernels
+            // (density_dense_kernel / force_gather_kernel: tile * 8), or -- row-staged density (SPH_DENSITY=rows) --
+            // its 32-particle passes become items (tile * 8 + 1 + pass) of the *_rows_items kernels.  Either way small
+            // grids on a second stream run them next to the main sweeps.
+            const int np = whole_tile_items ? 1 : (min(RB_THREADS, a.n - p0) + 31) / 32;
             const int q = atomicAdd(n_items, np);   // zeroed by reorder_kernel
-            for (int u = 0; u < np; ++u) items[q + u] = tile * 8 + 1 + u;
+            for (int u = 0; u < np; ++u) items[q + u] = tile * 8 + (whole_tile_items ? 0 : 1 + u);
         }
     }
 }
@@ -816,7 +817,8 @@ __device__ __forceinline__ void force_rows_tile(const SweepArgs &a, const GridDe
 // order, -1 padded.  Particles of planned tiles are decoded from the slot lists the sweeps really used; walk-path
 // particles and tiles taken as 32-particle passes (pass-local slots) are re-walked.
 __global__ void __launch_bounds__(128)
-neighbour_lists_kernel(const SweepArgs a, const GridDesc g, const StepConsts c, int32_t *__restrict__ out) {
+neighbour_lists_kernel(const SweepArgs a, const GridDesc g, const StepConsts c, int32_t *__restrict__ out,
+                       const uint32_t *__restrict__ dlist) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= a.n) return;
     const uint32_t key = a.skeys[t];
@@ -825,7 +827,11 @@ neighbour_lists_kernel(const SweepArgs a, const GridDesc g, const StepConsts c, 
     if (key == (uint32_t)g.ncells) return;
     const TilePlan &tp = a.plans[t / RB_THREADS];
     const uint8_t cf = a.ncnt[t];
-    if (g.aligned && tp.fits && !(cf & CNT_WALK)) {
+    if (g.aligned && !(cf & CNT_WALK) && !tp.fits && dlist) {   // dense tile: sorted indices (density_dense_kernel)
+        for (int k = 0; k < (int)cf; ++k) row[k] = (int32_t)a.sids[dlist[(size_t)t * kMaxNeighbours + k]];
+        return;
+    }
+    if (g.aligned && !(cf & CNT_WALK) && tp.fits) {
         int base[10];
         base[0] = 0;
         for (int r = 0; r < 9; ++r) base[r + 1] = base[r] + tp.row_len[r];

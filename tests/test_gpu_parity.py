@@ -272,11 +272,13 @@ def test_kernel_variants_agree(monkeypatch):
 
 
 @pytest.mark.parametrize("maker,n,arg,seed", [("dam", 60000, 2.5, 41), ("box", 50000, 2.5, 42), ("box", 50000, 8.0, 43),
-                                              ("box", 60000, 25.0, 44), ("box", 40000, 45.0, 45)])
+                                              ("box", 60000, 25.0, 44), ("box", 40000, 45.0, 45),
+                                              ("box", 40000, 111.0, 46), ("box", 60000, 260.0, 47)])
 def test_density_flat_equals_rows_bitwise(monkeypatch, maker, n, arg, seed):
     """density_flat_kernel (column blocks, packed superset scan; default) and the row-staged density sweep
-    (SPH_DENSITY=rows, also the fallback for tiles the flat kernel refuses: 45/cell overflows its staging) build the same
-    lists and the same canonical density sums: three steps agree bit for bit."""
+    (SPH_DENSITY=rows) build the same lists and the same canonical density sums: three steps agree bit for bit.  45 and
+    111 per cell (the reference's pipe density) run through the dense variant + force_gather_kernel, 260 per cell exceeds
+    even that staging (one-thread walks); the row-staged side takes those tiles as 32-particle passes / walks."""
     from cuda_sph_b200 import workloads
     params, st = (workloads.dam_break if maker == "dam" else workloads.uniform_box)(n, arg, seed)
     outs = []
@@ -366,7 +368,7 @@ def test_neighbour_lists_match_reference_golden(name):
 
 
 @pytest.mark.parametrize("maker,n,arg,seed", [("dam", 60000, 2.5, 51), ("box", 30000, 2.5, 52), ("box", 40000, 8.0, 53),
-                                              ("box", 40000, 60.0, 54)])
+                                              ("box", 40000, 60.0, 54), ("box", 40000, 140.0, 55)])
 def test_neighbour_lists_match_oracle(maker, n, arg, seed):
     """Same at sizes the reference cannot run: capped lists (dam-break column), sparse lists, and 60 per cell where the
     tiles are taken as 32-particle work items."""
