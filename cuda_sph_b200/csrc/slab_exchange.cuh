@@ -19,6 +19,7 @@
 namespace sph {
 
 constexpr int SLAB_MAX_WORLD = 16;
+constexpr int SLAB_FLAG_BYTES = 256;   // head of the receive allocation: one arrival flag per source rank
 constexpr int SLAB_HALO = 2;   // ghost columns per side (two: the density of first-column ghosts is recomputed locally)
 
 struct SlabRoute {
@@ -118,6 +119,90 @@ slab_route_kernel(SlabRoute r, float4 *__restrict__ pos_m, const float4 *__restr
     if (leaves) {   // the slot becomes a hole
         gid[i] = -1;
         pos_m[i] = make_float4(__int_as_float(0x7fc00000), 0.f, 0.f, 0.f);
+    }
+}
+
+// ---- fused routing: the force sweep's epilogue emits the records itself, straight into the receivers' memory ----------
+// With peer pointers (CUDA IPC handles of the receive buffers, sph_slab_open_peers) a rank does not pack a send buffer
+// at all: the thread that integrates a particle knows its new column, hence its new owner and the halos it falls into,
+// and stores the 32/48-byte record directly into the block "from me" of the destination's receive buffer over NVLink
+// (plain 16-byte stores to peer memory; slots come from LOCAL counters, warp-aggregated).  The transfer therefore rides
+// under the force sweep tile by tile, and the exchange that remains is slab_signal_wait_kernel: publish the record
+// counts, raise a flag at every peer, wait for theirs.  Receive buffers are double-buffered by exchange parity, so a
+// fast rank's next sweep never writes what a slow rank has not unpacked yet.
+struct SlabEmit {
+    SlabRoute r;
+    unsigned char *dst[SLAB_MAX_WORLD];   // my block in rank d's receive buffer of this parity (d == rank: my own)
+    int32_t *cnt;                         // [world][2] records emitted to rank d (migrants, ghosts); zeroed per step
+    int32_t *counters;                    // slab counters (overflow flags)
+    int32_t *gid;                         // global ids, writable: an emigrant's slot becomes a hole
+};
+
+__device__ __forceinline__ void slab_put(const SlabEmit &em, int d, int kind, const float4 &p, const float4 &v, int gid,
+                                         const uint64_t *rng) {
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned same = __match_any_sync(__activemask(), d * 2 + kind);   // lanes with a record for the same region
+    const int leader = __ffs(same) - 1;
+    int base = 0;
+    if ((int)lane == leader) base = atomicAdd(&em.cnt[d * 2 + kind], __popc(same));
+    base = __shfl_sync(same, base, leader);
+    const int mine = base + __popc(same & ((1u << lane) - 1u));
+    const int cap = kind == 0 ? em.r.cap_m[d] : em.r.cap_g[d];
+    if (mine >= cap) {
+        atomicOr(&em.counters[SLAB_OVERFLOW], 1);
+        return;
+    }
+    const int slot = kind == 0 ? mine : em.r.cap_m[d] + mine;
+    unsigned char *rec = em.dst[d] + 16 + (size_t)slot * em.r.rec_bytes;
+    *reinterpret_cast<float4 *>(rec) = p;
+    *reinterpret_cast<float4 *>(rec + 16) = make_float4(v.x, v.y, v.z, __int_as_float(gid));
+    if (em.r.rec_bytes == 48) {
+        uint64_t s0 = 0, s1 = 0;
+        if (kind == 0 && rng) {
+            s0 = rng[2 * (size_t)gid];
+            s1 = rng[2 * (size_t)gid + 1];
+        }
+        *reinterpret_cast<ulonglong2 *>(rec + 32) = make_ulonglong2(s0, s1);
+    }
+}
+
+// Same routing rule as slab_route_kernel, for ONE freshly integrated particle.  Returns true if the particle left the slab.
+__device__ __forceinline__ bool slab_emit_particle(const SlabEmit &em, const float4 &p, const float4 &v, int gid,
+                                                   const uint64_t *rng) {
+    const SlabRoute &r = em.r;
+    const int col = slab_column(p.x, r.voxel_x);
+    int o = r.rank;
+    if (col >= 0) o = slab_owner(r, col);   // a particle without a column (non-finite x) stays where it is, dead
+    const bool leaves = o != r.rank;
+    const int lo = r.bounds[o], hi = r.bounds[o + 1];
+    if (leaves) slab_put(em, o, 0, p, v, gid, rng);
+    if (o > 0 && col >= lo && col < lo + SLAB_HALO) slab_put(em, o - 1, 1, p, v, gid, nullptr);
+    if (o < r.world - 1 && col >= hi - SLAB_HALO && col < hi) slab_put(em, o + 1, 1, p, v, gid, nullptr);
+    return leaves;
+}
+
+// Exchange epilogue of a step: thread d publishes the counts of my block at rank d, raises my flag there (release at
+// system scope: the records were stored by the force sweep earlier in this stream) and waits for rank d's flag here.
+// flags[s] of a rank = last epoch rank s has completed.  The wait is bounded: a peer that never arrives (crashed
+// process) sets overflow bit 8 instead of hanging the GPU.
+__global__ void slab_signal_wait_kernel(const SlabEmit *__restrict__ em, int32_t *const *__restrict__ peer_flags,
+                                        volatile int32_t *my_flags, int epoch, long long timeout_cycles) {
+    const int d = threadIdx.x;
+    if (d >= em->r.world) return;
+    int32_t *hdr = reinterpret_cast<int32_t *>(em->dst[d]);
+    hdr[0] = em->cnt[d * 2];
+    hdr[1] = em->cnt[d * 2 + 1];
+    __threadfence_system();
+    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(peer_flags[d] + em->r.rank), "r"(epoch) : "memory");
+    const long long t0 = clock64();
+    for (;;) {
+        int v;
+        asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(my_flags + d) : "memory");
+        if (v - epoch >= 0) break;
+        if (clock64() - t0 > timeout_cycles) {
+            atomicOr(&em->counters[SLAB_OVERFLOW], 8);
+            break;
+        }
     }
 }
 

@@ -86,7 +86,17 @@ struct SphEngine {
     int64_t cell_capacity = 0;    // entries allocated in cell_range
     SlabRoute route{};            // native exchange (sph_slab_exchange_init)
     bool route_ready = false;
-    unsigned char *sendbuf = nullptr, *recvbuf = nullptr;
+    unsigned char *sendbuf = nullptr, *recvbuf = nullptr;   // recvbuf: parity 0, parity 1 back to back (inside recv_alloc)
+    unsigned char *recv_alloc = nullptr;   // [SLAB_FLAG_BYTES flags][receive buffer parity 0][parity 1]: the IPC-exported allocation
+    size_t xchg_bytes = 0;                 // one receive buffer
+    int parity = 0;                        // receive buffer the NEXT exchange fills
+    // fused routing over peer memory (sph_slab_open_peers)
+    bool p2p_ready = false;
+    void *peer_base[SLAB_MAX_WORLD]{};     // recv_alloc of every rank, mapped here (CUDA IPC); [rank] = my own
+    SlabEmit *emit_d = nullptr;            // [2] device copies, one per parity
+    int32_t **peer_flags_d = nullptr;      // [world] flag arrays of the peers
+    int32_t *emit_cnt = nullptr;           // [world][2]
+    int epoch = 0;
     int32_t *slab_counters = nullptr;   // SLAB_HWM, SLAB_NGHOST, SLAB_OVERFLOW, SLAB_SCRATCH, SLAB_NLIVE (+ pad)
     int32_t *tmp_gid = nullptr;         // compaction scratch
     // host-boundary staging (fp64 / fp32 (N,3) + rho), grown lazily
@@ -393,8 +403,11 @@ int sph_destroy(sph_handle_t e) {
     invalidate_graph(e);
     void *ptrs[] = {e->pos_m, e->vel_m, e->spos, e->svel, e->sforce, e->spress, e->svisc, e->srho, e->nlist, e->dlist, e->ncnt,
                     e->keys, e->ka, e->va, e->kb, e->vb, e->block_hist, e->digit_total, e->os_ctrl, e->tile_plans, e->refused, e->cell_range, e->pipe_d,
-                    e->rng, e->gid, e->stage, e->stats_d, e->snap_pos, e->snap_vel, e->snap_rng, e->sendbuf, e->recvbuf,
+                    e->rng, e->gid, e->stage, e->stats_d, e->snap_pos, e->snap_vel, e->snap_rng, e->sendbuf, e->recv_alloc, e->emit_d, e->peer_flags_d, e->emit_cnt,
                     e->slab_counters, e->tmp_gid};
+    if (e->p2p_ready)
+        for (int k = 0; k < e->route.world; ++k)
+            if (k != e->route.rank && e->peer_base[k]) cudaIpcCloseMemHandle(e->peer_base[k]);
     for (void *q : ptrs)
         if (q) cudaFree(q);
     for (auto &ev : e->ev)
@@ -505,6 +518,7 @@ static SweepArgs sweep_args(SphEngine *e, const uint32_t *sids, int n, int n_own
     sa.pipe = e->pipe_d;
     sa.rng = e->rng;
     sa.gid = e->slab ? e->gid : nullptr;
+    sa.emit = (e->slab && e->p2p_ready) ? e->emit_d + e->parity : nullptr;
     sa.n = n;
     sa.n_own = n_own;
     sa.plans = e->tile_plans;
@@ -521,6 +535,7 @@ static int enqueue_step(SphEngine *e, bool timed, int n, int n_own, int stages =
     cudaStream_t s = e->stream;
     const int g256 = (n + 255) / 256;
     const int ntiles = (n + RS_TILE - 1) / RS_TILE;
+    if (e->slab && e->p2p_ready) cudaMemsetAsync(e->emit_cnt, 0, sizeof(int32_t) * 2 * SLAB_MAX_WORLD, s);
     if (timed) cudaEventRecord(e->ev[0], s);
     if (stages & 1) hash_kernel<<<g256, 256, 0, s>>>(e->pos_m, e->keys, n, e->grid);
     if (timed) cudaEventRecord(e->ev[1], s);
@@ -1019,16 +1034,21 @@ int sph_slab_exchange_init(sph_handle_t e, int32_t world, int32_t rank, const in
         off += bytes;
     }
     r.peer_off[world] = off;
-    for (void *q : {(void *)e->sendbuf, (void *)e->recvbuf, (void *)e->slab_counters, (void *)e->tmp_gid})
+    if (e->p2p_ready) return fail("sph_slab_exchange_init after sph_slab_open_peers: create a new handle");
+    for (void *q : {(void *)e->sendbuf, (void *)e->recv_alloc, (void *)e->slab_counters, (void *)e->tmp_gid})
         if (q) cudaFree(q);
-    e->sendbuf = e->recvbuf = nullptr;
+    e->sendbuf = e->recvbuf = e->recv_alloc = nullptr;
+    off = (off + 255) & ~(int64_t)255;
+    e->xchg_bytes = (size_t)off;
+    e->parity = 0;
     e->slab_counters = e->tmp_gid = nullptr;
     CK(cudaMalloc((void **)&e->sendbuf, (size_t)off));
-    CK(cudaMalloc((void **)&e->recvbuf, (size_t)off));
+    CK(cudaMalloc((void **)&e->recv_alloc, SLAB_FLAG_BYTES + 2 * (size_t)off));
+    CK(cudaMemset(e->recv_alloc, 0, SLAB_FLAG_BYTES + 2 * (size_t)off));
+    e->recvbuf = e->recv_alloc + SLAB_FLAG_BYTES;
     CK(cudaMalloc((void **)&e->slab_counters, 8 * sizeof(int32_t)));
     CK(cudaMalloc((void **)&e->tmp_gid, sizeof(int32_t) * (size_t)own_cap));
     CK(cudaMemset(e->sendbuf, 0, (size_t)off));
-    CK(cudaMemset(e->recvbuf, 0, (size_t)off));
     CK(cudaMemset(e->slab_counters, 0, 8 * sizeof(int32_t)));
     // every slot starts empty
     CK(cudaMemset(e->gid, 0xff, sizeof(int32_t) * (size_t)e->n));
@@ -1066,10 +1086,79 @@ int sph_slab_unpack(sph_handle_t e) {
     int maxrec = 1;
     for (int k = 0; k < r.world; ++k) maxrec = std::max(maxrec, r.cap_m[k] + r.cap_g[k]);
     dim3 grid((maxrec + 255) / 256, r.world);
-    slab_unpack_kernel<<<grid, 256, 0, e->stream>>>(r, e->recvbuf, e->pos_m, e->vel_m, e->gid, e->rng,
-                                                    e->slab_counters);
+    slab_unpack_kernel<<<grid, 256, 0, e->stream>>>(r, e->recvbuf + (size_t)e->parity * e->xchg_bytes, e->pos_m, e->vel_m,
+                                                    e->gid, e->rng, e->slab_counters);
     CK(cudaGetLastError());
+    e->parity ^= 1;
     e->launches += 2;
+    return 0;
+}
+
+int sph_slab_parity(sph_handle_t e, int32_t *parity) {
+    if (check_route(e)) return 1;
+    if (!parity) return fail("null argument");
+    *parity = e->parity;
+    return 0;
+}
+
+int sph_slab_ipc_handle(sph_handle_t e, void *handle64) {
+    if (check_route(e)) return 1;
+    if (!handle64) return fail("null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    CK(cudaSetDevice(e->device));
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, e->recv_alloc));
+    memcpy(handle64, &h, 64);
+    return 0;
+}
+
+int sph_slab_open_peers(sph_handle_t e, const void *handles, const int64_t *remote_off) {
+    if (check_route(e)) return 1;
+    if (!handles || !remote_off) return fail("null argument");
+    if (e->p2p_ready) return fail("peers are already open");
+    CK(cudaSetDevice(e->device));
+    CK(cudaStreamSynchronize(e->stream));
+    const SlabRoute &r = e->route;
+    for (int k = 0; k < r.world; ++k) {
+        if (k == r.rank) {
+            e->peer_base[k] = e->recv_alloc;
+            continue;
+        }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const unsigned char *)handles + 64 * (size_t)k, 64);
+        CK(cudaIpcOpenMemHandle(&e->peer_base[k], h, cudaIpcMemLazyEnablePeerAccess));
+    }
+    CK(cudaMalloc((void **)&e->emit_d, 2 * sizeof(SlabEmit)));
+    CK(cudaMalloc((void **)&e->peer_flags_d, sizeof(int32_t *) * SLAB_MAX_WORLD));
+    CK(cudaMalloc((void **)&e->emit_cnt, sizeof(int32_t) * 2 * SLAB_MAX_WORLD));
+    SlabEmit em[2];
+    int32_t *flags[SLAB_MAX_WORLD] = {};
+    for (int q = 0; q < 2; ++q) {
+        em[q] = SlabEmit{};
+        em[q].r = r;
+        em[q].cnt = e->emit_cnt;
+        em[q].counters = e->slab_counters;
+        em[q].gid = e->gid;
+        for (int k = 0; k < r.world; ++k)   // every rank lays out its receive buffer by ITS block sizes: remote_off[k]
+            em[q].dst[k] = (unsigned char *)e->peer_base[k] + SLAB_FLAG_BYTES + (size_t)q * e->xchg_bytes + remote_off[k];
+    }
+    for (int k = 0; k < r.world; ++k) flags[k] = (int32_t *)e->peer_base[k];
+    CK(cudaMemcpy(e->emit_d, em, sizeof(em), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(e->peer_flags_d, flags, sizeof(flags), cudaMemcpyHostToDevice));
+    e->p2p_ready = true;
+    return 0;
+}
+
+// Exchange epilogue of a fused step: counts + flags to the peers, wait for theirs (slab_signal_wait_kernel).
+int sph_slab_barrier(sph_handle_t e) {
+    if (check_route(e)) return 1;
+    if (!e->p2p_ready) return fail("call sph_slab_open_peers first");
+    CK(cudaSetDevice(e->device));
+    e->epoch += 1;
+    slab_signal_wait_kernel<<<1, 32, 0, e->stream>>>(e->emit_d + e->parity, e->peer_flags_d, (volatile int32_t *)e->recv_alloc,
+                                                     e->epoch, 4000000000LL);
+    CK(cudaGetLastError());
+    e->launches += 1;
     return 0;
 }
 

@@ -20,6 +20,7 @@ tensors over gloo with the fp64 oracle as the local step and demands bitwise equ
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import List, Optional, Sequence
 
 import numpy as np
@@ -456,7 +457,7 @@ class NativeSlabRunner:
 
     def __init__(self, params, constants=None, *, col_hist: np.ndarray, bounds: Sequence[int], device: int = 0,
                  group=None, own_slack: float = 1.08, ghost_slack: float = 1.4, migrant_frac: float = 0.02,
-                 far_frac: float = 0.005, compact_every: int = 4, poll_every: int = 16):
+                 far_frac: float = 0.005, compact_every: int = 4, poll_every: int = 16, p2p: bool | None = None):
         from . import _lib
         from .strategy import SphConstants
         self._lib = _lib.load()
@@ -515,8 +516,17 @@ class NativeSlabRunner:
         self.block_bytes = [int(s) for s in sizes]
         dev = torch.device("cuda", device)
         total = int(sizes.sum())
+        stride = (total + 255) & ~255          # the receive buffer is double-buffered by exchange parity (sph_b200.h)
         self.send = torch.as_tensor(_CudaBuffer(sptr.value, (total,), "|u1"), device=dev)
-        self.recv = torch.as_tensor(_CudaBuffer(rptr.value, (total,), "|u1"), device=dev)
+        self.recv2 = [torch.as_tensor(_CudaBuffer(rptr.value + q * stride, (total,), "|u1"), device=dev) for q in (0, 1)]
+        # fused routing over peer memory: every rank maps the receive allocations of all ranks (CUDA IPC); the force
+        # sweep's epilogue then stores ghost / migrant records straight into them and a step needs no all_to_all
+        if p2p is None:
+            p2p = os.environ.get("SPH_SLAB_P2P", "1") != "0"
+        self.p2p = False
+        if p2p:
+            self._open_peers(col_hist, pipe_mode, dict(own_slack=own_slack, ghost_slack=ghost_slack,
+                                                       migrant_frac=migrant_frac, far_frac=far_frac), dev)
 
         def view(which, shape, typestr, dtype):
             ptr, cnt = C.c_void_p(), C.c_int64()
@@ -531,7 +541,45 @@ class NativeSlabRunner:
         self.R = view(5, (self.n_global, 2), "<i8", torch.int64) if pipe_mode else None   # xoroshiro128+ states by global id
         self.steps = 0
 
+    def _open_peers(self, col_hist, pipe_mode, slack, dev) -> None:
+        handle = np.zeros(64, np.uint8)
+        self._chk(self._lib.sph_slab_ipc_handle(self._h, handle.ctypes.data))
+        if self.world > 1:
+            mine = torch.as_tensor(handle).to(dev)
+            allh = [torch.empty_like(mine) for _ in range(self.world)]
+            dist.all_gather(allh, mine, group=self.group)
+            handles = np.ascontiguousarray(torch.stack(allh).cpu().numpy())
+        else:
+            handles = handle[None, :].copy()
+        # offset of the block "from me" inside rank k's receive buffer: rank k lays it out by ITS block sizes
+        remote = np.zeros(self.world, np.int64)
+        for k in range(self.world):
+            pk = plan_capacities(col_hist, self.bounds, k, self.n_global, pipe_mode, **slack)
+            rec = 48 if pipe_mode else 32
+            sizes_k = 16 + (pk["cap_m"].astype(np.int64) + pk["cap_g"].astype(np.int64)) * rec
+            remote[k] = int(sizes_k[:self.rank].sum())
+            assert int(sizes_k[self.rank]) == self.block_bytes[k], "block sizes must be symmetric"
+        self._chk(self._lib.sph_slab_open_peers(self._h, handles.ctypes.data, remote.ctypes.data))
+        self.p2p = True
+
     # ------------------------------------------------------------------ loading / stepping
+    def _parity(self) -> int:
+        q = C.c_int32()
+        self._chk(self._lib.sph_slab_parity(self._h, C.byref(q)))
+        return int(q.value)
+
+    def exchange(self) -> None:
+        """Rebuild halos and deliver migrants from the owned regions as they are: route -> one all_to_all -> unpack.
+        Every step of the all_to_all path; with peer memory only after loading / restoring a state."""
+        self._chk(self._lib.sph_slab_route(self._h))
+        recv = self.recv2[self._parity()]
+        if self.world > 1:
+            dist.all_to_all_single(recv, self.send, output_split_sizes=self.block_bytes,
+                                   input_split_sizes=self.block_bytes, group=self.group)
+        else:
+            recv.copy_(self.send)
+        self._chk(self._lib.sph_slab_unpack(self._h))
+
     def load_global(self, position: np.ndarray, velocity: np.ndarray) -> None:
         """Every rank passes the same full start state and keeps the particles of its slab (global id = row)."""
         q = np.asarray(position[:, 0], np.float64) / self.voxel_x
@@ -554,17 +602,19 @@ class NativeSlabRunner:
         self.counters.zero_()
         self.counters[0] = k
         self.steps = 0
+        self.exchange()
 
     def step(self, n_steps: int = 1) -> None:
+        """Between steps the state is AT REST: every particle sits with its owner and the ghost region holds the halos of
+        the current positions.  Peer memory: local step (the force sweep routes what it integrates into the receivers'
+        buffers) -> flag barrier -> unpack.  Otherwise: local step -> route -> all_to_all -> unpack."""
         for _ in range(n_steps):
-            self._chk(self._lib.sph_slab_route(self._h))
-            if self.world > 1:
-                dist.all_to_all_single(self.recv, self.send, output_split_sizes=self.block_bytes,
-                                       input_split_sizes=self.block_bytes, group=self.group)
-            else:
-                self.recv.copy_(self.send)
-            self._chk(self._lib.sph_slab_unpack(self._h))
             self._chk(self._lib.sph_slab_step_all(self._h))
+            if self.p2p:
+                self._chk(self._lib.sph_slab_barrier(self._h))
+                self._chk(self._lib.sph_slab_unpack(self._h))
+            else:
+                self.exchange()
             self.steps += 1
             if self.compact_every and self.steps % self.compact_every == 0:
                 self._chk(self._lib.sph_slab_compact(self._h))
@@ -592,22 +642,28 @@ class NativeSlabRunner:
     def step_timed(self) -> dict:
         """One step with CUDA events around every phase (synchronises; for the breakdown in bench.py, not for `value`)."""
         from . import _lib
+        t = _lib.SphTimings()
+        self._chk(self._lib.sph_slab_step_all_timed(self._h, C.byref(t)))
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
         ev[0].record()
-        self._chk(self._lib.sph_slab_route(self._h))
-        ev[1].record()
-        if self.world > 1:
-            dist.all_to_all_single(self.recv, self.send, output_split_sizes=self.block_bytes,
-                                   input_split_sizes=self.block_bytes, group=self.group)
+        if self.p2p:
+            ev[1].record()
+            self._chk(self._lib.sph_slab_barrier(self._h))
         else:
-            self.recv.copy_(self.send)
+            self._chk(self._lib.sph_slab_route(self._h))
+            ev[1].record()
+            recv = self.recv2[self._parity()]
+            if self.world > 1:
+                dist.all_to_all_single(recv, self.send, output_split_sizes=self.block_bytes,
+                                       input_split_sizes=self.block_bytes, group=self.group)
+            else:
+                recv.copy_(self.send)
         ev[2].record()
         self._chk(self._lib.sph_slab_unpack(self._h))
         ev[3].record()
-        t = _lib.SphTimings()
-        self._chk(self._lib.sph_slab_step_all_timed(self._h, C.byref(t)))
         torch.cuda.synchronize()
         self.steps += 1
+        # exchange_ms: the all_to_all, or (peer memory) the flag barrier = waiting for the slowest neighbour
         out = {"route_ms": ev[0].elapsed_time(ev[1]), "all_to_all_ms": ev[1].elapsed_time(ev[2]),
                "unpack_ms": ev[2].elapsed_time(ev[3])}
         out.update({k: getattr(t, k) for k in ("hash_ms", "sort_ms", "reorder_ms", "density_ms", "force_ms")})
@@ -626,6 +682,7 @@ class NativeSlabRunner:
         self.counters[2] = torch.maximum(overflow, snap[3][2])
         if snap[4] is not None:
             self.R.copy_(snap[4])
+        self.exchange()      # the ghost region belongs to another state: rebuild the halos (collective)
 
     # ------------------------------------------------------------------ inspection (these synchronise)
     def status(self) -> dict:
@@ -685,7 +742,7 @@ class NativeSlabRunner:
 
     def close(self):
         if getattr(self, "_h", None):
-            self.P = self.V = self.G = self.R = self.counters = self.send = self.recv = None
+            self.P = self.V = self.G = self.R = self.counters = self.send = self.recv2 = None
             self._lib.sph_destroy(self._h)
             self._h = None
 

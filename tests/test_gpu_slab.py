@@ -37,11 +37,13 @@ def _worker(rank, world, port, mode, n, steps, extra_steps, out_path, kind="nati
         cols = np.clip((st.position[:, 0] / params.voxel_size[0]).astype(np.int64), 0, n_cols - 1)
         hist = np.bincount(cols, minlength=n_cols)
         bounds = equal_count_bounds(hist, world)
-        if kind == "native":
+        if kind in ("native", "native_a2a"):
             # the pipe case moves two thirds of a rank's particles to the other rank in ONE step (outlet -> inlet
             # recycle at |v| ~ 1e2): size the migrant blocks for that
             run = NativeSlabRunner(params, SphConstants(mode=mode), col_hist=hist, bounds=bounds, device=rank,
-                                   compact_every=2, migrant_frac=1.0 if mode == "PIPE" else 0.05, own_slack=2.0)
+                                   compact_every=2, migrant_frac=1.0 if mode == "PIPE" else 0.05, own_slack=2.0,
+                                   p2p=(kind == "native"))
+            assert run.p2p == (kind == "native")
         else:
             run = GpuSlabRunner(params, SphConstants(mode=mode), capacity=2 * n, bounds=bounds, device=rank)
         run.load_global(st.position, st.velocity)
@@ -49,7 +51,7 @@ def _worker(rank, world, port, mode, n, steps, extra_steps, out_path, kind="nati
         assert run.count_global() == n
         pos, vel, rho = run.gather_global(n)
         if rank == 0:
-            if kind == "native":
+            if kind != "torch":
                 halo, migrated = run.status()["ghosts"], 1
             else:
                 halo, migrated = run.stats["halo_sent"], run.stats["migrated"]
@@ -73,7 +75,7 @@ def _case(mode, n):
     return params, type(st)(st.position, vel.astype(np.float32).astype(np.float64), st.density)
 
 
-@pytest.mark.parametrize("kind", ["native", "torch"])
+@pytest.mark.parametrize("kind", ["native", "native_a2a", "torch"])
 @pytest.mark.parametrize("mode,n,steps,extra", [("BOX", 200000, 3, 0), ("PIPE", 20000, 1, 2)])
 def test_two_gpu_slabs_equal_single_gpu(tmp_path, mode, n, steps, extra, kind):
     if torch.cuda.device_count() < 2:
@@ -96,10 +98,12 @@ def test_two_gpu_slabs_equal_single_gpu(tmp_path, mode, n, steps, extra, kind):
     assert got["halo"] > 0 and got["migrated"] > 0
 
 
+@pytest.mark.parametrize("p2p", [True, False])
 @pytest.mark.parametrize("mode,n,steps", [("BOX", 120000, 3), ("PIPE", 20000, 1)])
-def test_single_rank_native_slab_equals_plain_engine(mode, n, steps):
-    """World size 1 (runs on the driver's 1-GPU box): the slot layout with holes, slab_route / slab_unpack through the
-    self-exchange, the in-cell order repair by global id (fix_order_kernel) and the compaction must reproduce the plain
+def test_single_rank_native_slab_equals_plain_engine(mode, n, steps, p2p):
+    """World size 1 (runs on the driver's 1-GPU box): the slot layout with holes, the routing (p2p: fused into the force
+    sweep's epilogue, records stored straight into the receive buffer + flag barrier; else slab_route + self-copy),
+    slab_unpack, the in-cell order repair by global id (fix_order_kernel) and the compaction must reproduce the plain
     engine bit for bit -- BOX three steps (compaction after step 2), PIPE one step incl. the outlet -> inlet recycle."""
     from cuda_sph_b200 import B200SPHStrategy, SphConstants
     from cuda_sph_b200.slab import NativeSlabRunner
@@ -108,7 +112,7 @@ def test_single_rank_native_slab_equals_plain_engine(mode, n, steps):
     cols = np.clip((st.position[:, 0] / params.voxel_size[0]).astype(np.int64), 0, n_cols - 1)
     hist = np.bincount(cols, minlength=n_cols)
     run = NativeSlabRunner(params, SphConstants(mode=mode), col_hist=hist, bounds=[0, n_cols], device=0,
-                           compact_every=2, migrant_frac=1.0 if mode == "PIPE" else 0.05, own_slack=2.0)
+                           compact_every=2, migrant_frac=1.0 if mode == "PIPE" else 0.05, own_slack=2.0, p2p=p2p)
     # shuffle the slot order: arrival order on a slab is arbitrary, only the global ids define the in-cell order
     perm = np.random.default_rng(5).permutation(n)
     run.load_global(st.position, st.velocity)
