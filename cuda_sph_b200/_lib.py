@@ -75,7 +75,8 @@ EXPORTS = {
     "sph_slab_parity": (C.c_int, [_H, _P]),
     "sph_slab_ipc_handle": (C.c_int, [_H, _P]),
     "sph_slab_open_peers": (C.c_int, [_H, _P, _P]),
-    "sph_slab_barrier": (C.c_int, [_H]),
+    "sph_slab_exchange_p2p": (C.c_int, [_H]),
+    "sph_slab_exchange_p2p_timed": (C.c_int, [_H, _P]),
     "sph_get_keys": (C.c_int, [_H, _P]),
     "sph_get_sorted_ids": (C.c_int, [_H, _P]),
     "sph_get_sorted_keys": (C.c_int, [_H, _P]),

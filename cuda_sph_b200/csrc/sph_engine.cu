@@ -94,6 +94,7 @@ struct SphEngine {
     bool p2p_ready = false;
     void *peer_base[SLAB_MAX_WORLD]{};     // recv_alloc of every rank, mapped here (CUDA IPC); [rank] = my own
     SlabEmit *emit_d = nullptr;            // [2] device copies, one per parity
+    SlabEmit emit_h[2]{};                  // the same on the host (kernel parameters of the route / push kernels)
     int32_t **peer_flags_d = nullptr;      // [world] flag arrays of the peers
     int32_t *emit_cnt = nullptr;           // [world][2]
     int epoch = 0;
@@ -518,7 +519,6 @@ static SweepArgs sweep_args(SphEngine *e, const uint32_t *sids, int n, int n_own
     sa.pipe = e->pipe_d;
     sa.rng = e->rng;
     sa.gid = e->slab ? e->gid : nullptr;
-    sa.emit = (e->slab && e->p2p_ready) ? e->emit_d + e->parity : nullptr;
     sa.n = n;
     sa.n_own = n_own;
     sa.plans = e->tile_plans;
@@ -535,7 +535,6 @@ static int enqueue_step(SphEngine *e, bool timed, int n, int n_own, int stages =
     cudaStream_t s = e->stream;
     const int g256 = (n + 255) / 256;
     const int ntiles = (n + RS_TILE - 1) / RS_TILE;
-    if (e->slab && e->p2p_ready) cudaMemsetAsync(e->emit_cnt, 0, sizeof(int32_t) * 2 * SLAB_MAX_WORLD, s);
     if (timed) cudaEventRecord(e->ev[0], s);
     if (stages & 1) hash_kernel<<<g256, 256, 0, s>>>(e->pos_m, e->keys, n, e->grid);
     if (timed) cudaEventRecord(e->ev[1], s);
@@ -1138,28 +1137,54 @@ int sph_slab_open_peers(sph_handle_t e, const void *handles, const int64_t *remo
         em[q].r = r;
         em[q].cnt = e->emit_cnt;
         em[q].counters = e->slab_counters;
-        em[q].gid = e->gid;
-        for (int k = 0; k < r.world; ++k)   // every rank lays out its receive buffer by ITS block sizes: remote_off[k]
-            em[q].dst[k] = (unsigned char *)e->peer_base[k] + SLAB_FLAG_BYTES + (size_t)q * e->xchg_bytes + remote_off[k];
+        em[q].inv_vx = (float)(1.0 / r.voxel_x);
+        em[q].in_lo = r.bounds[r.rank] + (r.rank > 0 ? SLAB_HALO : 0);
+        em[q].in_hi = r.bounds[r.rank + 1] - (r.rank < r.world - 1 ? SLAB_HALO : 0);
+        for (int k = 0; k < r.world; ++k) em[q].src[k] = e->sendbuf + r.peer_off[k];
+        for (int k = 0; k < r.world; ++k)   // every rank lays out its two receive buffers by ITS block sizes
+            em[q].dst[k] = (unsigned char *)e->peer_base[k] + SLAB_FLAG_BYTES + remote_off[2 * k + q];
     }
     for (int k = 0; k < r.world; ++k) flags[k] = (int32_t *)e->peer_base[k];
     CK(cudaMemcpy(e->emit_d, em, sizeof(em), cudaMemcpyHostToDevice));
+    e->emit_h[0] = em[0];
+    e->emit_h[1] = em[1];
     CK(cudaMemcpy(e->peer_flags_d, flags, sizeof(flags), cudaMemcpyHostToDevice));
     e->p2p_ready = true;
     return 0;
 }
 
-// Exchange epilogue of a fused step: counts + flags to the peers, wait for theirs (slab_signal_wait_kernel).
-int sph_slab_barrier(sph_handle_t e) {
+// The exchange over peer memory: route (CTA-aggregated) -> push the used records into the receivers' buffers -> counts +
+// flags to the peers, wait for theirs.  sph_slab_unpack follows.
+static int exchange_p2p(SphEngine *e, float *ms3) {
     if (check_route(e)) return 1;
     if (!e->p2p_ready) return fail("call sph_slab_open_peers first");
     CK(cudaSetDevice(e->device));
     e->epoch += 1;
-    slab_signal_wait_kernel<<<1, 32, 0, e->stream>>>(e->emit_d + e->parity, e->peer_flags_d, (volatile int32_t *)e->recv_alloc,
-                                                     e->epoch, 4000000000LL);
+    const SlabRoute &r = e->route;
+    cudaStream_t s = e->stream;
+    if (ms3) cudaEventRecord(e->ev[0], s);
+    CK(cudaMemsetAsync(e->emit_cnt, 0, sizeof(int32_t) * 2 * SLAB_MAX_WORLD, s));
+    slab_route_cta_kernel<<<(r.own_cap + ROUTE_CTA - 1) / ROUTE_CTA, ROUTE_CTA, 0, s>>>(e->emit_h[e->parity], e->pos_m,
+                                                                                      e->vel_m, e->gid, e->rng);
+    if (ms3) cudaEventRecord(e->ev[1], s);
+    slab_push_kernel<<<dim3(PUSH_CTAS, r.world), 256, 0, s>>>(e->emit_h[e->parity]);
+    if (ms3) cudaEventRecord(e->ev[2], s);
+    slab_signal_wait_kernel<<<1, 32, 0, s>>>(e->emit_d + e->parity, e->peer_flags_d, (volatile int32_t *)e->recv_alloc,
+                                             e->epoch, 4000000000LL);
+    if (ms3) cudaEventRecord(e->ev[3], s);
     CK(cudaGetLastError());
-    e->launches += 1;
+    e->launches += 4;
+    if (ms3) {
+        CK(cudaEventSynchronize(e->ev[3]));
+        for (int k = 0; k < 3; ++k) CK(cudaEventElapsedTime(&ms3[k], e->ev[k], e->ev[k + 1]));
+    }
     return 0;
+}
+int sph_slab_exchange_p2p(sph_handle_t e) { return exchange_p2p(e, nullptr); }
+/* same with CUDA events around the three kernels: ms3 = {route, push, flag barrier}; synchronises */
+int sph_slab_exchange_p2p_timed(sph_handle_t e, float *ms3) {
+    if (!ms3) return fail("null argument");
+    return exchange_p2p(e, ms3);
 }
 
 int sph_slab_step_all(sph_handle_t e) {

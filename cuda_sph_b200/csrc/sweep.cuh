@@ -26,7 +26,6 @@
 // virtual list does not fit 16-bit indices take a plain one-thread-per-particle walk instead.
 #pragma once
 #include "collide.cuh"
-#include "slab_exchange.cuh"
 #include "sph_common.cuh"
 
 namespace sph {
@@ -56,7 +55,6 @@ struct SweepArgs {
     const double *pipe;
     uint64_t *rng;
     const int32_t *gid;   // x-slab mode: global particle id per local index (rng states are indexed by it); else null
-    const SlabEmit *emit; // x-slab mode with peer pointers: the epilogue routes the particle itself (slab_exchange.cuh)
     int n;                // local particles (owned + ghosts)
     int n_own;            // local indices < n_own are owned: only those are integrated and written back
 };
@@ -174,14 +172,8 @@ __device__ __forceinline__ void finish_particle(const SweepArgs &a, const StepCo
     } else {
         collide_box(x, v, c);
     }
-    float4 pn = make_float4((float)x[0], (float)x[1], (float)x[2], rho_i);
-    const float4 vn = make_float4((float)v[0], (float)v[1], (float)v[2], 0.f);
-    if (a.emit && slab_emit_particle(*a.emit, pn, vn, a.gid[id], a.rng)) {   // left the slab: the slot becomes a hole
-        a.emit->gid[id] = -1;
-        pn = make_float4(__int_as_float(0x7fc00000), 0.f, 0.f, 0.f);
-    }
-    a.pos_m[id] = pn;
-    a.vel_m[id] = vn;
+    a.pos_m[id] = make_float4((float)x[0], (float)x[1], (float)x[2], rho_i);
+    a.vel_m[id] = make_float4((float)v[0], (float)v[1], (float)v[2], 0.f);
     a.sforce[t] = make_float4((float)F[0], (float)F[1], (float)F[2], 0.f);
     if (RECORD_TERMS) {
         a.spress[t] = make_float4(f.px, f.py, f.pz, 0.f);

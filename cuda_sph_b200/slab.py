@@ -519,8 +519,8 @@ class NativeSlabRunner:
         stride = (total + 255) & ~255          # the receive buffer is double-buffered by exchange parity (sph_b200.h)
         self.send = torch.as_tensor(_CudaBuffer(sptr.value, (total,), "|u1"), device=dev)
         self.recv2 = [torch.as_tensor(_CudaBuffer(rptr.value + q * stride, (total,), "|u1"), device=dev) for q in (0, 1)]
-        # fused routing over peer memory: every rank maps the receive allocations of all ranks (CUDA IPC); the force
-        # sweep's epilogue then stores ghost / migrant records straight into them and a step needs no all_to_all
+        # exchange over peer memory: every rank maps the receive allocations of all ranks (CUDA IPC) and pushes its
+        # ghost / migrant records straight into them (route -> push -> flag barrier kernels): a step needs no all_to_all
         if p2p is None:
             p2p = os.environ.get("SPH_SLAB_P2P", "1") != "0"
         self.p2p = False
@@ -552,12 +552,14 @@ class NativeSlabRunner:
         else:
             handles = handle[None, :].copy()
         # offset of the block "from me" inside rank k's receive buffer: rank k lays it out by ITS block sizes
-        remote = np.zeros(self.world, np.int64)
+        remote = np.zeros(2 * self.world, np.int64)
         for k in range(self.world):
             pk = plan_capacities(col_hist, self.bounds, k, self.n_global, pipe_mode, **slack)
             rec = 48 if pipe_mode else 32
             sizes_k = 16 + (pk["cap_m"].astype(np.int64) + pk["cap_g"].astype(np.int64)) * rec
-            remote[k] = int(sizes_k[:self.rank].sum())
+            stride_k = (int(sizes_k.sum()) + 255) & ~255       # rank k's second receive buffer starts here
+            remote[2 * k] = int(sizes_k[:self.rank].sum())
+            remote[2 * k + 1] = stride_k + remote[2 * k]
             assert int(sizes_k[self.rank]) == self.block_bytes[k], "block sizes must be symmetric"
         self._chk(self._lib.sph_slab_open_peers(self._h, handles.ctypes.data, remote.ctypes.data))
         self.p2p = True
@@ -569,8 +571,12 @@ class NativeSlabRunner:
         return int(q.value)
 
     def exchange(self) -> None:
-        """Rebuild halos and deliver migrants from the owned regions as they are: route -> one all_to_all -> unpack.
-        Every step of the all_to_all path; with peer memory only after loading / restoring a state."""
+        """Deliver migrants and rebuild the halos from the owned regions as they are.  Peer memory: route -> push into the
+        receivers' buffers -> flag barrier (three kernels, no collective); otherwise route -> one all_to_all.  Then unpack."""
+        if self.p2p:
+            self._chk(self._lib.sph_slab_exchange_p2p(self._h))
+            self._chk(self._lib.sph_slab_unpack(self._h))
+            return
         self._chk(self._lib.sph_slab_route(self._h))
         recv = self.recv2[self._parity()]
         if self.world > 1:
@@ -606,15 +612,10 @@ class NativeSlabRunner:
 
     def step(self, n_steps: int = 1) -> None:
         """Between steps the state is AT REST: every particle sits with its owner and the ghost region holds the halos of
-        the current positions.  Peer memory: local step (the force sweep routes what it integrates into the receivers'
-        buffers) -> flag barrier -> unpack.  Otherwise: local step -> route -> all_to_all -> unpack."""
+        the current positions.  A step = local step -> exchange (peer memory or all_to_all) -> unpack."""
         for _ in range(n_steps):
             self._chk(self._lib.sph_slab_step_all(self._h))
-            if self.p2p:
-                self._chk(self._lib.sph_slab_barrier(self._h))
-                self._chk(self._lib.sph_slab_unpack(self._h))
-            else:
-                self.exchange()
+            self.exchange()
             self.steps += 1
             if self.compact_every and self.steps % self.compact_every == 0:
                 self._chk(self._lib.sph_slab_compact(self._h))
@@ -646,9 +647,11 @@ class NativeSlabRunner:
         self._chk(self._lib.sph_slab_step_all_timed(self._h, C.byref(t)))
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
         ev[0].record()
+        ms3 = None
         if self.p2p:
             ev[1].record()
-            self._chk(self._lib.sph_slab_barrier(self._h))
+            ms3 = np.zeros(3, np.float32)
+            self._chk(self._lib.sph_slab_exchange_p2p_timed(self._h, ms3.ctypes.data))
         else:
             self._chk(self._lib.sph_slab_route(self._h))
             ev[1].record()
@@ -666,6 +669,8 @@ class NativeSlabRunner:
         # exchange_ms: the all_to_all, or (peer memory) the flag barrier = waiting for the slowest neighbour
         out = {"route_ms": ev[0].elapsed_time(ev[1]), "all_to_all_ms": ev[1].elapsed_time(ev[2]),
                "unpack_ms": ev[2].elapsed_time(ev[3])}
+        if ms3 is not None:   # peer memory: no all_to_all; the exchange is three kernels
+            out.update(route_ms=float(ms3[0]), all_to_all_ms=0.0, push_ms=float(ms3[1]), flag_barrier_ms=float(ms3[2]))
         out.update({k: getattr(t, k) for k in ("hash_ms", "sort_ms", "reorder_ms", "density_ms", "force_ms")})
         return out
 

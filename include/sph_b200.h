@@ -156,19 +156,21 @@ int sph_slab_step_all_timed(sph_handle_t h, SphTimings *t); /* same, with per-st
 int sph_slab_compact(sph_handle_t h);
 int sph_slab_counters(sph_handle_t h, int32_t *out5);
 
-/* Fused routing over peer memory (csrc/slab_exchange.cuh "fused routing"): the receive buffer is double-buffered by
- * exchange parity -- *recvbuf of sph_slab_exchange_init points at buffer 0, buffer 1 follows at
+/* Exchange over peer memory (csrc/slab_exchange.cuh "exchange over peer memory"): the receive buffer is double-buffered
+ * by exchange parity -- *recvbuf of sph_slab_exchange_init points at buffer 0, buffer 1 follows at
  * (sum(block_bytes) rounded up to 256) bytes; sph_slab_unpack consumes buffer `parity` and flips it, an all_to_all of the
  * host layer must therefore land in buffer sph_slab_parity().  With the receive allocations of all ranks mapped
- * (sph_slab_ipc_handle -> all-gather of the 64-byte CUDA IPC handles -> sph_slab_open_peers; remote_off[k] = byte offset
- * of the block "from this rank" inside rank k's receive buffer), sph_slab_step_all routes every particle it integrates
- * from the force sweep's epilogue straight into the owners' / neighbours' receive buffers over NVLink, and a step is
- *   sph_slab_step_all -> sph_slab_barrier (counts + arrival flags to all peers, wait for theirs) -> sph_slab_unpack;
- * sph_slab_route + all_to_all + sph_slab_unpack remain the way to (re)build the halos of a freshly loaded state. */
+ * (sph_slab_ipc_handle -> all-gather of the 64-byte CUDA IPC handles -> sph_slab_open_peers; remote_off[2 k + q] = byte
+ * offset of the block "from this rank" inside rank k's receive buffers, q = 0 / 1 the parity: ranks differ in size) a
+ * step needs no collective:
+ *   sph_slab_step_all -> sph_slab_exchange_p2p (CTA-aggregated routing into the send blocks, used records pushed into
+ *   the receivers' buffers over NVLink, counts + arrival flags to all peers, bounded wait for theirs) -> sph_slab_unpack;
+ * sph_slab_route + all_to_all + sph_slab_unpack remain the portable path (and what the host layer uses without IPC). */
 int sph_slab_parity(sph_handle_t h, int32_t *parity);
 int sph_slab_ipc_handle(sph_handle_t h, void *handle64);
-int sph_slab_open_peers(sph_handle_t h, const void *handles /* world x 64 bytes */, const int64_t *remote_off);
-int sph_slab_barrier(sph_handle_t h);
+int sph_slab_open_peers(sph_handle_t h, const void *handles /* world x 64 bytes */, const int64_t *remote_off /* 2 x world */);
+int sph_slab_exchange_p2p(sph_handle_t h);
+int sph_slab_exchange_p2p_timed(sph_handle_t h, float *ms3); /* + CUDA events: {route, push, flag barrier} ms; synchronises */
 
 /* ---- parity taps: state of the most recent step --------------------------------------------------------------- */
 int sph_get_keys(sph_handle_t h, int32_t *keys);                 /* self.voxels            voxel_sph_strategy.py:82 */
