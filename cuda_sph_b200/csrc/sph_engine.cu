@@ -68,6 +68,8 @@ struct SphEngine {
     cudaStream_t aux_stream = nullptr;   // the work-item kernels run here, next to the main sweeps
     cudaEvent_t ev_fork[2]{}, ev_join[2]{};
     bool flat_density = true;         // SPH_DENSITY=rows: every tile through density_rows_kernel
+    int dense_min_slots = RB_CAP * 3 / 2;   // non-fitting tiles with longer rows go to the dense kernels whatever their
+                                          // cell count (measured: 2304 costs dam1m +40 %, 4096 costs pipe4m +60 %)
     uint32_t *os_ctrl = nullptr;      // onesweep control block (histograms, tickets, look-back status)
     bool onesweep = true;         // SPH_SORT=classic selects the three-kernel passes of radix_sort.cuh
     bool sort_lookback = false;   // SPH_SORT=lookback: decoupled look-back passes (one kernel per digit) instead of count + scan
@@ -234,6 +236,7 @@ int sph_create(const SphParams *params, int device, sph_handle_t *out) {
     }
     if (const char *sw = getenv("SPH_SWEEP")) e->rows_sweeps = strcmp(sw, "warp") != 0;
     if (const char *sd = getenv("SPH_DENSITY")) e->flat_density = strcmp(sd, "rows") != 0;
+    if (const char *sd = getenv("SPH_DENSE_MIN_SLOTS")) e->dense_min_slots = atoi(sd);
     e->slab = (params->flags & SPH_FLAG_SLAB) != 0;
     long long table_cells = ncells;
     if (e->slab) {
@@ -323,7 +326,7 @@ int sph_create(const SphParams *params, int device, sph_handle_t *out) {
     ALLOC(e->os_ctrl, os_ctrl_words(e->passes, (n + OS_TILE - 1) / OS_TILE));
     ALLOC(e->tile_plans, (n + RB_THREADS - 1) / RB_THREADS);
     e->ntiles_rb = (n + RB_THREADS - 1) / RB_THREADS;
-    ALLOC(e->refused, 5 * (size_t)e->ntiles_rb + 2);
+    ALLOC(e->refused, 6 * (size_t)e->ntiles_rb + 4);
     ALLOC(e->cell_range, e->cell_capacity);
     if (e->slab) ALLOC(e->gid, n);
     ALLOC(e->stats_d, 4);
@@ -522,8 +525,10 @@ static SweepArgs sweep_args(SphEngine *e, const uint32_t *sids, int n, int n_own
     sa.n = n;
     sa.n_own = n_own;
     sa.plans = e->tile_plans;
-    sa.n_items = e->refused;
-    sa.items = e->refused + 2;
+    sa.n_items = e->refused;       // [0] passes (list A), [1] tiles refused by density_flat_kernel (B), [2] dense tiles (C)
+    sa.items = e->refused + 4;
+    sa.n_dense = e->refused + 2;
+    sa.dense_items = e->refused + 4 + 5 * (size_t)e->ntiles_rb;
     return sa;
 }
 
@@ -611,18 +616,18 @@ static int enqueue_step(SphEngine *e, bool timed, int n, int n_own, int stages =
     if (e->rows_sweeps) {
         const int grb = (n + RB_THREADS - 1) / RB_THREADS;
         cudaStream_t x = e->aux_stream;
-        int *list_b = e->refused + 2 + 4 * (size_t)e->ntiles_rb;
+        int *list_b = e->refused + 4 + 4 * (size_t)e->ntiles_rb;
         if (stages & 2) {
             rows_plan_kernel<<<(grb + RP_WARPS - 1) / RP_WARPS, RP_WARPS * 32, 0, s>>>(
-                sa, e->grid, e->tile_plans, grb, e->refused, e->refused + 2, e->flat_density ? 1 : 0);
+                sa, e->grid, e->tile_plans, grb, e->refused, e->refused + 4, e->refused + 2,
+                e->refused + 4 + 5 * (size_t)e->ntiles_rb, e->flat_density ? DENSE_MAX_CELLS : 0, e->dense_min_slots);
             // fork: the tiles whose rows do not fit run next to the main density sweep
             cudaEventRecord(e->ev_fork[0], s);
             cudaStreamWaitEvent(x, e->ev_fork[0], 0);
             if (e->flat_density)
                 density_dense_kernel<<<148 * 3, DN_THREADS, sizeof(DenseSmem), x>>>(sa, e->grid, e->consts, e->dlist);
-            else
-                density_rows_items_kernel<<<ITEM_CTAS, RB_THREADS, sizeof(DensityRowsSmem), x>>>(sa, e->grid, e->consts,
-                                                                                                 sa.n_items, sa.items);
+            density_rows_items_kernel<<<ITEM_CTAS, RB_THREADS, sizeof(DensityRowsSmem), x>>>(sa, e->grid, e->consts,
+                                                                                             sa.n_items, sa.items);
             cudaEventRecord(e->ev_join[0], x);
             if (e->flat_density) {
                 const FlatArgs fa{list_b, e->refused + 1};
@@ -641,15 +646,13 @@ static int enqueue_step(SphEngine *e, bool timed, int n, int n_own, int stages =
             if (e->spress) {
                 if (e->flat_density)
                     force_gather_kernel<true><<<148 * 8, RB_THREADS, 0, x>>>(sa, e->grid, e->consts, e->dlist);
-                else
-                    force_rows_items_kernel<true><<<ITEM_CTAS, RB_THREADS, sizeof(ForceRowsSmem), x>>>(sa, e->grid, e->consts);
+                force_rows_items_kernel<true><<<ITEM_CTAS, RB_THREADS, sizeof(ForceRowsSmem), x>>>(sa, e->grid, e->consts);
                 cudaEventRecord(e->ev_join[1], x);
                 force_rows_kernel<true><<<grb, RB_THREADS, sizeof(ForceRowsSmem), s>>>(sa, e->grid, e->consts);
             } else {
                 if (e->flat_density)
                     force_gather_kernel<false><<<148 * 8, RB_THREADS, 0, x>>>(sa, e->grid, e->consts, e->dlist);
-                else
-                    force_rows_items_kernel<false><<<ITEM_CTAS, RB_THREADS, sizeof(ForceRowsSmem), x>>>(sa, e->grid, e->consts);
+                force_rows_items_kernel<false><<<ITEM_CTAS, RB_THREADS, sizeof(ForceRowsSmem), x>>>(sa, e->grid, e->consts);
                 cudaEventRecord(e->ev_join[1], x);
                 force_rows_kernel<false><<<grb, RB_THREADS, sizeof(ForceRowsSmem), s>>>(sa, e->grid, e->consts);
             }

@@ -29,7 +29,7 @@ reorder_kernel(const uint32_t *__restrict__ skeys, const uint32_t *__restrict__ 
                float4 *__restrict__ svel, int2 *__restrict__ cell_range, int n, int *__restrict__ n_items) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
-    if (t == 0) n_items[0] = n_items[1] = 0;   // work-item counters of the sweeps (rows_plan_kernel / density_flat_kernel)
+    if (t == 0) n_items[0] = n_items[1] = n_items[2] = 0;   // work-item counters of the sweeps (rows_plan_kernel / density_flat_kernel)
     const uint32_t key = skeys[t];
     const uint32_t id = sids[t];
     if (t == 0) {

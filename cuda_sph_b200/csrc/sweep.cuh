@@ -43,6 +43,8 @@ struct SweepArgs {
     const TilePlan *plans;   // row-staged sweeps: one plan per 128-particle tile (rows_plan_kernel)
     const int *n_items;      // work items of the sweeps: the 32-particle passes of tiles whose rows do not fit
     const int *items;        //   tile * 8 + 1 + pass
+    const int *n_dense;      // ... and the tiles of a few dense cells (sweep_dense.cuh): tile * 8
+    const int *dense_items;
     const float4 *spos;
     const float4 *svel;
     const uint32_t *skeys;

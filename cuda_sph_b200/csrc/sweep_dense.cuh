@@ -23,6 +23,7 @@ namespace sph {
 
 constexpr int DN_THREADS = RB_THREADS;
 constexpr int DN_CHUNK = 2048;                 // candidates staged per chunk
+constexpr int DENSE_MAX_CELLS = 3;             // tiles of at most this many cells (> 42 particles per cell) come here
 constexpr int DN_MROWS = FL_KEEP + 1;          // non-zero masks per lane (+ one spare row)
 static_assert(DN_CHUNK % (4 * DN_THREADS) == 0, "staging runs four candidates per thread and trip");
 
@@ -241,9 +242,9 @@ __global__ void __launch_bounds__(DN_THREADS, 3)
 density_dense_kernel(const SweepArgs a, const GridDesc g, const StepConsts c, uint32_t *__restrict__ dlist) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     DenseSmem &sm = *reinterpret_cast<DenseSmem *>(smem_raw);
-    const int n = *a.n_items;
+    const int n = *a.n_dense;
     for (int i = blockIdx.x; i < n; i += gridDim.x) {
-        dense_tile(a, g, c, dlist, a.items[i] >> 3, sm);
+        dense_tile(a, g, c, dlist, a.dense_items[i] >> 3, sm);
         __syncthreads();
     }
 }
@@ -254,10 +255,10 @@ density_dense_kernel(const SweepArgs a, const GridDesc g, const StepConsts c, ui
 template <bool RECORD>
 __global__ void __launch_bounds__(RB_THREADS)
 force_gather_kernel(const SweepArgs a, const GridDesc g, const StepConsts c, const uint32_t *__restrict__ dlist) {
-    const int n = *a.n_items;
+    const int n = *a.n_dense;
     const int j = threadIdx.x;
     for (int i = blockIdx.x; i < n; i += gridDim.x) {
-        const int tile = a.items[i] >> 3;
+        const int tile = a.dense_items[i] >> 3;
         const int t = tile * RB_THREADS + j;
         if (t >= a.n) continue;
         const uint32_t key = a.skeys[t];

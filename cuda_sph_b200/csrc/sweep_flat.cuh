@@ -288,28 +288,51 @@ density_flat_kernel(const SweepArgs a, const GridDesc g, const StepConsts c, con
     }
     __syncthreads();
 
-    // ---- stage: eight lanes per segment, up to four independent 16-B loads per lane and trip -------------------------
+    // ---- stage: eight lanes per segment.  A trip takes FOUR segments: their first eight candidates are loaded together
+    //      (at <= 8 particles per cell that is all of them: four independent 16-B loads in flight per lane instead of one
+    //      load per trip), longer segments finish in a tail of up to three more loads per lane -----------------------------
     {
         const int sub = lane & 7;
-        for (int it = j >> 3; it < nseg; it += FL_THREADS / 8) {
-            const int n = sm.u.st.seg_n[it];
-            if (n == 0) continue;
-            const int gs = sm.u.st.seg_g[it], f0 = sm.u.st.seg_f[it];
-            const int s = it % 9;
-            const int slot0 = sm.row_base[s] + (gs - sm.row_lo[s]);
-            for (int q0 = sub; q0 < n; q0 += 32) {
-                float4 v[4];
+        for (int it0 = j >> 3; it0 < nseg; it0 += 4 * (FL_THREADS / 8)) {
+            int n[4], gs[4], f0[4], slot0[4];
+            float4 v[4];
 #pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    if (q0 + 8 * u < n) v[u] = __ldg(&a.spos[gs + q0 + 8 * u]);
+            for (int u = 0; u < 4; ++u) {
+                const int it = it0 + u * (FL_THREADS / 8);
+                n[u] = (it < nseg) ? (int)sm.u.st.seg_n[it] : 0;
+                if (n[u]) {
+                    gs[u] = sm.u.st.seg_g[it];
+                    f0[u] = sm.u.st.seg_f[it];
+                    const int s = it % 9;
+                    slot0[u] = sm.row_base[s] + (gs[u] - sm.row_lo[s]);
+                    if (sub < n[u]) v[u] = __ldg(&a.spos[gs[u] + sub]);
+                }
+            }
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int q = q0 + 8 * u;
-                    if (q < n) {
-                        sm.x[f0 + q] = v[u].x;
-                        sm.y[f0 + q] = v[u].y;
-                        sm.z[f0 + q] = v[u].z;
-                        sm.slot[f0 + q] = (uint16_t)(slot0 + q);
+            for (int u = 0; u < 4; ++u) {
+                if (sub < n[u]) {
+                    sm.x[f0[u] + sub] = v[u].x;
+                    sm.y[f0[u] + sub] = v[u].y;
+                    sm.z[f0[u] + sub] = v[u].z;
+                    sm.slot[f0[u] + sub] = (uint16_t)(slot0[u] + sub);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                for (int q0 = sub + 8; q0 < n[u]; q0 += 24) {
+                    float4 w[3];
+#pragma unroll
+                    for (int k = 0; k < 3; ++k)
+                        if (q0 + 8 * k < n[u]) w[k] = __ldg(&a.spos[gs[u] + q0 + 8 * k]);
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        const int q = q0 + 8 * k;
+                        if (q < n[u]) {
+                            sm.x[f0[u] + q] = w[k].x;
+                            sm.y[f0[u] + q] = w[k].y;
+                            sm.z[f0[u] + q] = w[k].z;
+                            sm.slot[f0[u] + q] = (uint16_t)(slot0[u] + q);
+                        }
                     }
                 }
             }

@@ -38,10 +38,16 @@ namespace sph {
 #endif
 constexpr int RB_THREADS = SPH_RB_THREADS;   // threads == particles per CTA (a tile)
 constexpr int RB_WARPS = RB_THREADS / 32;
-constexpr int RB_CAP = RB_THREADS == 128 ? 2048 : RB_THREADS == 64 ? 1536 : 3328;   // row slots per CTA pass (candidates staged in shared memory)
+#ifndef SPH_RB_CAP
+#define SPH_RB_CAP (RB_THREADS == 128 ? 2048 : RB_THREADS == 64 ? 1536 : 3328)
+#endif
+constexpr int RB_CAP = SPH_RB_CAP;   // row slots per CTA pass (candidates staged in shared memory)
 constexpr int RB_MAXC = RB_THREADS / 2;                   // non-empty cells per CTA pass
 constexpr int RB_DENSITY_CTAS = RB_THREADS == 128 ? 4 : RB_THREADS == 64 ? 6 : 2;   // CTAs per SM the kernels are sized for
-constexpr int RB_FORCE_CTAS = RB_THREADS == 128 ? 3 : RB_THREADS == 64 ? 4 : 2;
+#ifndef SPH_RB_FORCE_CTAS
+#define SPH_RB_FORCE_CTAS (RB_THREADS == 128 ? 3 : RB_THREADS == 64 ? 4 : 2)
+#endif
+constexpr int RB_FORCE_CTAS = SPH_RB_FORCE_CTAS;
 constexpr int RB_KEEP = 33;       // superset candidates kept per particle (32 + spares for rejected band candidates)
 constexpr int RB_LSTRIDE = 38;    // uint16 per list row (19 words: conflict-free rows; >= RB_KEEP + 1)
 
@@ -233,7 +239,8 @@ constexpr int ITEM_CTAS = 148 * 2;   // grid of the work-item kernels
 
 __global__ void __launch_bounds__(RP_WARPS * 32)
 rows_plan_kernel(const SweepArgs a, const GridDesc g, TilePlan *__restrict__ plans, int ntiles,
-                 int *__restrict__ n_items, int *__restrict__ items, int whole_tile_items) {
+                 int *__restrict__ n_items, int *__restrict__ items, int *__restrict__ n_dense,
+                 int *__restrict__ dense_items, int dense_max_cells, int dense_min_slots) {
     const int lane = threadIdx.x & 31;
     const int tile = blockIdx.x * RP_WARPS + (threadIdx.x >> 5);
     if (tile >= ntiles) return;
@@ -288,13 +295,20 @@ rows_plan_kernel(const SweepArgs a, const GridDesc g, TilePlan *__restrict__ pla
         const bool fits = sum <= RB_CAP && ncell <= RB_MAXC;
         tp.fits = fits ? 1 : 0;
         if (!fits && g.aligned) {
-            // rows that do not fit the sweeps' shared-memory staging: the tile becomes a work item of the dense kernels
-            // (density_dense_kernel / force_gather_kernel: tile * 8), or -- row-staged density (SPH_DENSITY=rows) --
-            // its 32-particle passes become items (tile * 8 + 1 + pass) of the *_rows_items kernels.  Either way small
-            // grids on a second stream run them next to the main sweeps.
-            const int np = whole_tile_items ? 1 : (min(RB_THREADS, a.n - p0) + 31) / 32;
-            const int q = atomicAdd(n_items, np);   // zeroed by reorder_kernel
-            for (int u = 0; u < np; ++u) items[q + u] = tile * 8 + (whole_tile_items ? 0 : 1 + u);
+            // rows that do not fit the sweeps' shared-memory staging.  A tile of a few dense cells becomes a work item of the
+            // dense kernels (density_dense_kernel / force_gather_kernel, one cell at a time: slots < 0 marks it); a
+            // tile of many cells -- or any tile with the row-staged density (SPH_DENSITY=rows) -- is taken as 32-particle
+            // passes (tile * 8 + 1 + pass) by the *_rows_items kernels.  Either way small grids on a second stream run
+            // them next to the main sweeps.
+            // (rows far beyond the staging mean dense neighbour cells: 32-particle passes would not fit either)
+            if (dense_max_cells > 0 && (ncell <= dense_max_cells || sum > dense_min_slots)) {
+                tp.slots = -max(sum, 1);
+                dense_items[atomicAdd(n_dense, 1)] = tile * 8;   // counters are zeroed by reorder_kernel
+            } else {
+                const int np = (min(RB_THREADS, a.n - p0) + 31) / 32;
+                const int q = atomicAdd(n_items, np);
+                for (int u = 0; u < np; ++u) items[q + u] = tile * 8 + 1 + u;
+            }
         }
     }
 }
@@ -827,7 +841,7 @@ neighbour_lists_kernel(const SweepArgs a, const GridDesc g, const StepConsts c, 
     if (key == (uint32_t)g.ncells) return;
     const TilePlan &tp = a.plans[t / RB_THREADS];
     const uint8_t cf = a.ncnt[t];
-    if (g.aligned && !(cf & CNT_WALK) && !tp.fits && dlist) {   // dense tile: sorted indices (density_dense_kernel)
+    if (g.aligned && !(cf & CNT_WALK) && !tp.fits && tp.slots < 0 && dlist) {   // dense tile: sorted indices (density_dense_kernel)
         for (int k = 0; k < (int)cf; ++k) row[k] = (int32_t)a.sids[dlist[(size_t)t * kMaxNeighbours + k]];
         return;
     }
