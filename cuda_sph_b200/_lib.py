@@ -95,6 +95,7 @@ EXPORTS = {
     "sph_get_frame_stats": (C.c_int, [_H, C.POINTER(SphFrameStats)]),
     "sph_export_stats": (C.c_int, [_H, C.c_int32, C.POINTER(SphFrameStats)]),
     "sph_n_cells": (C.c_int64, [_H]),
+    "sph_path_counters": (C.c_int, [_H, _P]),
     "sph_cell_dims": (C.c_int, [_H, _P, _P]),
     "sph_device_ptr": (C.c_int, [_H, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
     "sph_launch_count": (C.c_int64, [_H]),
@@ -116,7 +117,11 @@ def load():
                            "(there is no CPU fallback)")
         lib = C.CDLL(LIB_PATH)
         for name, (res, args) in EXPORTS.items():
-            fn = getattr(lib, name)
+            fn = getattr(lib, name, None)
+            if fn is None:
+                if os.environ.get("SPH_B200_LIB"):   # an A/B variant library built from an older tree
+                    continue
+                raise SphError(f"{LIB_PATH} lacks the symbol {name}: rebuild it (python -m cuda_sph_b200.build)")
             fn.restype, fn.argtypes = res, args
         _lib = lib
     return _lib

@@ -55,6 +55,28 @@ os_hist(const uint32_t *__restrict__ keys, int n, OsPasses ps, uint32_t *__restr
     }
 }
 
+// hash_kernel + os_hist in one pass over the positions (assign_voxels_to_particles_kernel, voxel_kernels.py:88-105, and
+// the digit histograms of every pass of the sort that follows): the keys are written once and not read back here.
+__global__ void __launch_bounds__(OS_THREADS)
+hash_hist_kernel(const float4 *__restrict__ pos_m, uint32_t *__restrict__ keys, int n, GridDesc g, OsPasses ps,
+                 uint32_t *__restrict__ ctrl) {
+    __shared__ uint32_t hist[OS_MAX_PASSES][OS_RADIX];
+    const int tid = threadIdx.x;
+    for (int p = 0; p < ps.n_passes; ++p) hist[p][tid] = 0;
+    __syncthreads();
+    for (int i = blockIdx.x * OS_THREADS + tid; i < n; i += gridDim.x * OS_THREADS) {
+        const float4 q = pos_m[i];
+        const uint32_t k = key_of(g, q.x, q.y, q.z);
+        keys[i] = k;
+        for (int p = 0; p < ps.n_passes; ++p) atomicAdd(&hist[p][(k >> ps.shift[p]) & ps.mask[p]], 1u);
+    }
+    __syncthreads();
+    for (int p = 0; p < ps.n_passes; ++p) {
+        const uint32_t v = hist[p][tid];
+        if (v) atomicAdd(&ctrl[p * OS_RADIX + tid], v);
+    }
+}
+
 // peers of this lane's digit (8 bits) among the valid lanes, by ballots
 __device__ __forceinline__ uint32_t os_match(uint32_t d, bool valid) {
     uint32_t peers = __ballot_sync(0xffffffffu, valid);
@@ -275,6 +297,171 @@ ts_scatter(const uint32_t *__restrict__ kin, const uint32_t *__restrict__ vin, u
             const uint32_t dst = wcnt[warp][d] + rank[k];
             kout[dst] = key[k];
             vout[dst] = vin ? vin[i] : (uint32_t)i;
+        }
+    }
+}
+
+
+// ---- second generation pass (the default): tile sorted in shared memory, coalesced scatter --------------------------------
+// The passes above store every pair straight from its register to its final place: 4-byte stores to (up to) 32 different
+// sectors per warp instruction, which is what bounds them (ncu: 0.48 ms per pass at 2^25 pairs, 1.1 TB/s).  Here a tile
+// is first sorted by its digit INSIDE shared memory (stable: position = digit start in the tile + pairs of the earlier
+// warps + rank inside the warp), then written out in that order, so that consecutive threads write consecutive
+// addresses of a digit's run (16 pairs = 64 B on average at 4096-pair tiles and 256 digits).  Ranks come from
+// match.any (one instruction instead of eight ballots).  LOOKBACK selects how a tile learns its global offsets:
+// decoupled look-back over the status words (one launch per pass) or the per-tile counts of ts2_hist + ts_scan.
+constexpr int OS2_ITEMS = 16;
+constexpr int OS2_TILE = OS_THREADS * OS2_ITEMS;   // 4096 pairs per tile
+
+struct Os2Smem {
+    uint32_t wcnt[OS_WARPS][OS_RADIX];   // per-warp digit counts, then the warp's first local position of a digit
+    uint32_t delta[OS_RADIX];            // global position of a pair = delta[digit] + its position in the sorted tile
+    uint32_t skey[OS2_TILE], sval[OS2_TILE];
+    uint32_t warp_sum[OS_WARPS], warp_sum2[OS_WARPS];
+    int tile;
+};
+
+__global__ void __launch_bounds__(OS_THREADS)
+ts2_hist(const uint32_t *__restrict__ keys, int n, int shift, uint32_t mask, uint32_t *__restrict__ tile_cnt,
+         int ntiles) {
+    __shared__ uint32_t hist[OS_RADIX];
+    const int tid = threadIdx.x;
+    hist[tid] = 0;
+    __syncthreads();
+    const int base = blockIdx.x * OS2_TILE;
+#pragma unroll
+    for (int k = 0; k < OS2_ITEMS; ++k) {
+        const int i = base + k * OS_THREADS + tid;
+        if (i < n) atomicAdd(&hist[(keys[i] >> shift) & mask], 1u);
+    }
+    __syncthreads();
+    tile_cnt[(size_t)tid * ntiles + blockIdx.x] = hist[tid];
+}
+
+template <bool LOOKBACK>
+__global__ void __launch_bounds__(OS_THREADS, 3)
+os2_pass(const uint32_t *__restrict__ kin, const uint32_t *__restrict__ vin, uint32_t *__restrict__ kout,
+         uint32_t *__restrict__ vout, int n, int pass, int n_passes, int shift, uint32_t mask, int ntiles,
+         uint32_t *__restrict__ ctrl, const uint32_t *__restrict__ tile_off) {
+    extern __shared__ __align__(16) unsigned char os2_raw[];
+    Os2Smem &sm = *reinterpret_cast<Os2Smem *>(os2_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (LOOKBACK && tid == 0) sm.tile = (int)atomicAdd(&ctrl[n_passes * OS_RADIX + pass], 1u);
+#pragma unroll
+    for (int w = 0; w < OS_WARPS; ++w) sm.wcnt[w][tid] = 0;
+    __syncthreads();
+    const int tile = LOOKBACK ? sm.tile : (int)blockIdx.x;
+    const int nvalid = min(OS2_TILE, n - tile * OS2_TILE);
+
+    // the warp's 512 pairs, 32 at a time in input order: stable rank among the warp's pairs of the same digit
+    const int wbase = tile * OS2_TILE + warp * (32 * OS2_ITEMS);
+    uint32_t key[OS2_ITEMS], val[OS2_ITEMS], rank2[OS2_ITEMS / 2];   // two 16-bit ranks per register
+    const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll
+    for (int k = 0; k < OS2_ITEMS; ++k) {
+        const int i = wbase + k * 32 + lane;
+        key[k] = (i < n) ? kin[i] : 0u;
+    }
+#pragma unroll
+    for (int k = 0; k < OS2_ITEMS; ++k) {
+        const int i = wbase + k * 32 + lane;
+        val[k] = (i < n) ? (vin ? vin[i] : (uint32_t)i) : 0u;
+    }
+#pragma unroll
+    for (int k = 0; k < OS2_ITEMS; ++k) {
+        const int i = wbase + k * 32 + lane;
+        const bool valid = i < n;
+        const uint32_t d = (key[k] >> shift) & mask;
+        const uint32_t peers = __match_any_sync(0xffffffffu, valid ? d : (0x10000u + lane));
+        uint32_t pre = 0;
+        if (valid) pre = sm.wcnt[warp][d];
+        __syncwarp();
+        if (valid && (peers & lt) == 0) sm.wcnt[warp][d] = pre + __popc(peers);
+        __syncwarp();
+        const uint32_t r = pre + __popc(peers & lt);
+        rank2[k >> 1] = (k & 1) ? (rank2[k >> 1] | (r << 16)) : r;
+    }
+    __syncthreads();
+
+    // digit `tid`: count in this tile, start inside the sorted tile, global offset
+    uint32_t tile_cnt = 0;
+#pragma unroll
+    for (int w = 0; w < OS_WARPS; ++w) tile_cnt += sm.wcnt[w][tid];
+    uint32_t gbase;   // global position of the tile's first pair of digit `tid`
+    if (LOOKBACK) {
+        volatile uint32_t *status = ctrl + (size_t)n_passes * OS_RADIX + 8 + ((size_t)pass * ntiles) * OS_RADIX;
+        uint32_t excl = 0;
+        if (tile == 0) {
+            status[tid] = OS_FLAG_PREFIX | tile_cnt;
+        } else {
+            status[(size_t)tile * OS_RADIX + tid] = OS_FLAG_AGG | tile_cnt;
+            int prev = tile - 1;
+            while (true) {
+                const uint32_t s = status[(size_t)prev * OS_RADIX + tid];
+                const uint32_t flag = s & ~OS_VALUE_MASK;
+                if (flag == 0) continue;   // predecessor has a ticket, hence is resident or done: it will publish
+                excl += s & OS_VALUE_MASK;
+                if (flag == OS_FLAG_PREFIX) break;
+                --prev;
+            }
+            status[(size_t)tile * OS_RADIX + tid] = OS_FLAG_PREFIX | (excl + tile_cnt);
+        }
+        const uint32_t tot = ctrl[pass * OS_RADIX + tid];   // exclusive scan of the 256 global digit totals
+        uint32_t inc = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += u;
+        }
+        if (lane == 31) sm.warp_sum[warp] = inc;
+        gbase = inc - tot + excl;
+    } else {
+        gbase = tile_off[(size_t)tid * ntiles + tile];
+    }
+    uint32_t linc = tile_cnt;   // exclusive scan of the tile's digit counts
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t u = __shfl_up_sync(0xffffffffu, linc, o);
+        if (lane >= o) linc += u;
+    }
+    if (lane == 31) sm.warp_sum2[warp] = linc;
+    __syncthreads();
+    uint32_t lstart = linc - tile_cnt;
+#pragma unroll
+    for (int w = 0; w < OS_WARPS; ++w) {
+        if (w < warp) {
+            lstart += sm.warp_sum2[w];
+            if (LOOKBACK) gbase += sm.warp_sum[w];
+        }
+    }
+    sm.delta[tid] = gbase - lstart;
+    uint32_t running = lstart;   // per-warp first positions (warp order == input order)
+#pragma unroll
+    for (int w = 0; w < OS_WARPS; ++w) {
+        const uint32_t c = sm.wcnt[w][tid];
+        sm.wcnt[w][tid] = running;
+        running += c;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < OS2_ITEMS; ++k) {
+        const int i = wbase + k * 32 + lane;
+        if (i < n) {
+            const uint32_t d = (key[k] >> shift) & mask;
+            const uint32_t p = sm.wcnt[warp][d] + ((rank2[k >> 1] >> ((k & 1) * 16)) & 0xffffu);
+            sm.skey[p] = key[k];
+            sm.sval[p] = val[k];
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < OS2_ITEMS; ++k) {
+        const int p = k * OS_THREADS + tid;
+        if (p < nvalid) {
+            const uint32_t kk = sm.skey[p];
+            const uint32_t dst = sm.delta[(kk >> shift) & mask] + (uint32_t)p;
+            kout[dst] = kk;
+            vout[dst] = sm.sval[p];
         }
     }
 }

@@ -72,7 +72,8 @@ struct SphEngine {
                                           // cell count (measured: 2304 costs dam1m +40 %, 4096 costs pipe4m +60 %)
     uint32_t *os_ctrl = nullptr;      // onesweep control block (histograms, tickets, look-back status)
     bool onesweep = true;         // SPH_SORT=classic selects the three-kernel passes of radix_sort.cuh
-    bool sort_lookback = false;   // SPH_SORT=lookback: decoupled look-back passes (one kernel per digit) instead of count + scan
+    bool sort_gen2 = true;        // tiles sorted in shared memory + coalesced scatter, hash fused with the histograms (SPH_SORT=count|lookback: first generation)
+    bool sort_lookback = true;   // SPH_SORT=lookback: decoupled look-back passes (one kernel per digit) instead of count + scan
     int ntiles = 0, passes = 0, pass_bits[8]{}, key_bits = 0;
     int2 *cell_range = nullptr;
     // pipe
@@ -320,7 +321,10 @@ int sph_create(const SphParams *params, int device, sph_handle_t *out) {
     ALLOC(e->digit_total, RS_RADIX);
     if (const char *so = getenv("SPH_SORT")) {
         e->onesweep = strcmp(so, "classic") != 0;
-        e->sort_lookback = strcmp(so, "lookback") == 0;
+        // lookback2 (default) | count2: second generation, tile offsets by decoupled look-back | per-tile counts + scan;
+        // lookback | count: first generation (register-to-global scatter); classic: three-kernel passes of radix_sort.cuh
+        e->sort_lookback = strcmp(so, "lookback") == 0 || strcmp(so, "lookback2") == 0;
+        e->sort_gen2 = strcmp(so, "lookback2") == 0 || strcmp(so, "count2") == 0;
     }
     if (e->passes > OS_MAX_PASSES) e->onesweep = false;
     ALLOC(e->os_ctrl, os_ctrl_words(e->passes, (n + OS_TILE - 1) / OS_TILE));
@@ -377,6 +381,8 @@ int sph_create(const SphParams *params, int device, sph_handle_t *out) {
         }
     }
     for (auto &ev : e->ev) cudaEventCreate(&ev);
+    cudaFuncSetAttribute(os2_pass<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Os2Smem));
+    cudaFuncSetAttribute(os2_pass<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Os2Smem));
     cudaFuncSetAttribute(density_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DensityRowsSmem));
     cudaFuncSetAttribute(density_flat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FlatSmem));
     cudaFuncSetAttribute(density_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DenseSmem));
@@ -390,7 +396,7 @@ int sph_create(const SphParams *params, int device, sph_handle_t *out) {
                          (int)sizeof(ForceRowsSmem));
     cudaFuncSetAttribute(force_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)sizeof(ForceRowsSmem));
-    e->launches_per_step = 1 + (e->onesweep ? 2 + (e->sort_lookback ? 1 : 3) * e->passes : 3 * e->passes) + 1 + 1 + 1 + 1 +
+    e->launches_per_step = ((e->onesweep && e->sort_gen2) ? 0 : 1) + (e->onesweep ? 2 + (e->sort_lookback ? 1 : 3) * e->passes : 3 * e->passes) + 1 + 1 + 1 + 1 +
                            (e->rows_sweeps ? (e->flat_density ? 4 : 3) : 0);
     if (cudaDeviceSynchronize() != cudaSuccess) {
         sph_destroy(e);
@@ -541,10 +547,50 @@ static int enqueue_step(SphEngine *e, bool timed, int n, int n_own, int stages =
     const int g256 = (n + 255) / 256;
     const int ntiles = (n + RS_TILE - 1) / RS_TILE;
     if (timed) cudaEventRecord(e->ev[0], s);
-    if (stages & 1) hash_kernel<<<g256, 256, 0, s>>>(e->pos_m, e->keys, n, e->grid);
-    if (timed) cudaEventRecord(e->ev[1], s);
-    // LSD radix sort of (key, id): pass 0 reads keys with implicit iota values
+    const bool gen2 = e->onesweep && e->sort_gen2;
     if (!(stages & 1)) {
+    } else if (gen2) {
+        // second-generation sort: hash + digit histograms of every pass in one kernel, then one (look-back) or three
+        // (count, scan, scatter) launches per 8-bit digit with 4096-pair tiles sorted in shared memory
+        const int otiles = (n + OS2_TILE - 1) / OS2_TILE;
+        OsPasses ps{};
+        ps.n_passes = e->passes;
+        int shift = 0;
+        for (int p = 0; p < e->passes; ++p) {
+            ps.shift[p] = shift;
+            ps.mask[p] = (1u << e->pass_bits[p]) - 1u;
+            shift += e->pass_bits[p];
+        }
+        cudaMemsetAsync(e->os_ctrl, 0,
+                        sizeof(uint32_t) * (e->sort_lookback ? os_ctrl_words(e->passes, otiles)
+                                                             : (size_t)e->passes * OS_RADIX + 8), s);
+        hash_hist_kernel<<<std::min((n + OS_THREADS - 1) / OS_THREADS, 148 * 8), OS_THREADS, 0, s>>>(
+            e->pos_m, e->keys, n, e->grid, ps, e->os_ctrl);
+        if (timed) cudaEventRecord(e->ev[1], s);
+        const uint32_t *kin = e->keys, *vin = nullptr;
+        uint32_t *tile_cnt = e->os_ctrl + (size_t)e->passes * OS_RADIX + 8;
+        for (int p = 0; p < e->passes; ++p) {
+            uint32_t *kout = (p % 2 == 0) ? e->ka : e->kb;
+            uint32_t *vout = (p % 2 == 0) ? e->va : e->vb;
+            if (e->sort_lookback) {
+                os2_pass<true><<<otiles, OS_THREADS, sizeof(Os2Smem), s>>>(kin, vin, kout, vout, n, p, e->passes,
+                                                                            ps.shift[p], ps.mask[p], otiles, e->os_ctrl,
+                                                                            nullptr);
+            } else {
+                ts2_hist<<<otiles, OS_THREADS, 0, s>>>(kin, n, ps.shift[p], ps.mask[p], tile_cnt, otiles);
+                ts_scan<<<OS_RADIX, OS_THREADS, 0, s>>>(tile_cnt, otiles, e->os_ctrl + p * OS_RADIX);
+                os2_pass<false><<<otiles, OS_THREADS, sizeof(Os2Smem), s>>>(kin, vin, kout, vout, n, p, e->passes,
+                                                                             ps.shift[p], ps.mask[p], otiles, e->os_ctrl,
+                                                                             tile_cnt);
+            }
+            kin = kout;
+            vin = vout;
+        }
+    }
+    if ((stages & 1) && !gen2) hash_kernel<<<g256, 256, 0, s>>>(e->pos_m, e->keys, n, e->grid);
+    if (timed && !((stages & 1) && gen2)) cudaEventRecord(e->ev[1], s);
+    // LSD radix sort of (key, id): pass 0 reads keys with implicit iota values
+    if (!(stages & 1) || gen2) {
     } else if (e->onesweep) {
         const int otiles = (n + OS_TILE - 1) / OS_TILE;
         OsPasses ps{};
@@ -1373,6 +1419,18 @@ int sph_get_stats(sph_handle_t e, SphStats *st) {
     return 0;
 }
 int64_t sph_n_cells(sph_handle_t e) { return e ? e->grid.ncells : -1; }
+int sph_path_counters(sph_handle_t e, int32_t *out4) {
+    if (!e || !out4) return fail("null argument");
+    CK(cudaSetDevice(e->device));
+    int h[3] = {0, 0, 0};
+    CK(cudaMemcpyAsync(h, e->refused, sizeof(h), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    out4[0] = h[0];
+    out4[1] = h[1];
+    out4[2] = h[2];
+    out4[3] = e->ntiles_rb;
+    return 0;
+}
 int sph_cell_dims(sph_handle_t e, int32_t *ceil3, int32_t *trunc3) {
     if (!e) return fail("null handle");
     for (int d = 0; d < 3; ++d) {

@@ -53,10 +53,8 @@ struct FlatSmem {
     float x[FL_CAP + FL_SLACK], y[FL_CAP + FL_SLACK], z[FL_CAP + FL_SLACK];
     uint16_t slot[FL_CAP];               // staged position -> row slot of the force sweep
     union {
-        struct {                              // staging tables, dead once the candidates are staged
-            int seg_g[FL_MAXB * 9];           // first sorted index of segment (block, dy, dz)
-            uint16_t seg_n[FL_MAXB * 9];      // its length
-            uint16_t seg_f[FL_MAXB * 9];      // its staged position
+        struct {                              // staging table, dead once the candidates are staged: segment (block, dy, dz)
+            int4 seg[FL_MAXB * 9];            // = (first sorted index, length, staged position, first row slot)
         } st;
         // per thread: its NON-ZERO hit masks in scan order (first candidate of a round in bit 31); one spare row so the
         // second pass may read one word ahead
@@ -140,6 +138,14 @@ density_flat_kernel(const SweepArgs a, const GridDesc g, const StepConsts c, con
     if (j < 9) {
         rlen = tp.row_len[j];
         rlo = tp.row_lo[j];
+    }
+    {   // streaming inputs of the tile that runs PF_AHEAD CTAs later -> L2
+        const int pp0 = (tile + PF_AHEAD) * FL_THREADS;
+        if (pp0 + FL_THREADS <= a.n && j >= 32 && j < 32 + 21) {
+            if (j == 32) prefetch_l2(&a.plans[tile + PF_AHEAD]);
+            else if (j < 32 + 5) prefetch_l2(reinterpret_cast<const char *>(a.skeys + pp0) + (j - 33) * 128);
+            else prefetch_l2(reinterpret_cast<const char *>(a.spos + pp0) + (j - 37) * 128);
+        }
     }
     const bool live = key != (uint32_t)g.ncells;
     if (j < nb && !live) {   // dead particle: no neighbours
@@ -228,18 +234,32 @@ density_flat_kernel(const SweepArgs a, const GridDesc g, const StepConsts c, con
     }
     __syncthreads();
 
-    // ---- segments: the 9 cell ranges of every block ------------------------------------------------------------------
+    // ---- segments: the 9 cell ranges of every block; the range loads of all trips are issued together ----------------
     const int nseg = refuse ? 0 : nblk * 9;
-    for (int it = j; it < nseg; it += FL_THREADS) {
-        const int b = it / 9, s = it - b * 9;
-        const int x = sm.blk_x[b], y = sm.blk_cy[b] + s / 3 - 1, z = sm.blk_cz[b] + s % 3 - 1;
-        int2 r = make_int2(0, 0);
-        if (y >= 0 && y < g.ty && z >= 0 && z < g.tz) {
-            const long long cl = (long long)x - g.xoff + (long long)y * g.wn + (long long)z * g.wn * g.hn;
-            if (cl >= 0 && cl < g.ncells) r = __ldg(&a.cell_range[cl]);
+    {
+        constexpr int SEG_TRIPS = (FL_MAXB * 9 + FL_THREADS - 1) / FL_THREADS;
+        int2 rr[SEG_TRIPS];
+#pragma unroll
+        for (int u = 0; u < SEG_TRIPS; ++u) {
+            const int it = j + u * FL_THREADS;
+            rr[u] = make_int2(0, 0);
+            if (it < nseg) {
+                const int b = it / 9, s = it - b * 9;
+                const int x = sm.blk_x[b], y = sm.blk_cy[b] + s / 3 - 1, z = sm.blk_cz[b] + s % 3 - 1;
+                if (y >= 0 && y < g.ty && z >= 0 && z < g.tz) {
+                    const long long cl = (long long)x - g.xoff + (long long)y * g.wn + (long long)z * g.wn * g.hn;
+                    if (cl >= 0 && cl < g.ncells) rr[u] = __ldg(&a.cell_range[cl]);
+                }
+            }
         }
-        sm.u.st.seg_g[it] = r.x;
-        sm.u.st.seg_n[it] = (uint16_t)min(max(r.y - r.x, 0), FL_CAP + 1);
+#pragma unroll
+        for (int u = 0; u < SEG_TRIPS; ++u) {
+            const int it = j + u * FL_THREADS;
+            if (it < nseg) {
+                sm.u.st.seg[it].x = rr[u].x;
+                sm.u.st.seg[it].y = min(max(rr[u].y - rr[u].x, 0), FL_CAP + 1);
+            }
+        }
     }
     __syncthreads();
 
@@ -247,7 +267,7 @@ density_flat_kernel(const SweepArgs a, const GridDesc g, const StepConsts c, con
     int tot = 0;
     if (j < nseg / 9) {
 #pragma unroll
-        for (int s = 0; s < 9; ++s) tot += sm.u.st.seg_n[j * 9 + s];
+        for (int s = 0; s < 9; ++s) tot += sm.u.st.seg[j * 9 + s].y;
     }
     const int padded = (tot + 3) & ~3;
     int sinc = padded;
@@ -275,9 +295,11 @@ density_flat_kernel(const SweepArgs a, const GridDesc g, const StepConsts c, con
         if (j == nblk - 1) sm.blk_start[nblk] = start + padded;
         int f = start;
 #pragma unroll
-        for (int s = 0; s < 9; ++s) {
-            sm.u.st.seg_f[j * 9 + s] = (uint16_t)f;
-            f += sm.u.st.seg_n[j * 9 + s];
+        for (int s = 0; s < 9; ++s) {   // complete the segment descriptors: staged position, first row slot
+            int4 &d = sm.u.st.seg[j * 9 + s];
+            d.z = f;
+            d.w = sm.row_base[s] + (d.x - sm.row_lo[s]);
+            f += d.y;
         }
         for (; f < start + padded; ++f) {   // pad candidates: far away, never a hit
             sm.x[f] = 1e18f;
@@ -288,55 +310,46 @@ density_flat_kernel(const SweepArgs a, const GridDesc g, const StepConsts c, con
     }
     __syncthreads();
 
-    // ---- stage: eight lanes per segment.  A trip takes FOUR segments: their first eight candidates are loaded together
-    //      (at <= 8 particles per cell that is all of them: four independent 16-B loads in flight per lane instead of one
-    //      load per trip), longer segments finish in a tail of up to three more loads per lane -----------------------------
+    // ---- stage: eight lanes per segment, every candidate by three 4-byte cp.async (x | y | z land transposed without a
+    //      register round trip, so ALL copies of the tile are in flight before the first one is waited for; the first
+    //      version loaded float4s into registers and stored them, which exposed one global round trip per trip of the loop)
     {
         const int sub = lane & 7;
-        for (int it0 = j >> 3; it0 < nseg; it0 += 4 * (FL_THREADS / 8)) {
-            int n[4], gs[4], f0[4], slot0[4];
-            float4 v[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int it = it0 + u * (FL_THREADS / 8);
-                n[u] = (it < nseg) ? (int)sm.u.st.seg_n[it] : 0;
-                if (n[u]) {
-                    gs[u] = sm.u.st.seg_g[it];
-                    f0[u] = sm.u.st.seg_f[it];
-                    const int s = it % 9;
-                    slot0[u] = sm.row_base[s] + (gs[u] - sm.row_lo[s]);
-                    if (sub < n[u]) v[u] = __ldg(&a.spos[gs[u] + sub]);
-                }
+        auto stage_segment = [&](const int4 d) {   // (first sorted index, length, staged position, first row slot)
+            if (sub < d.y) {   // the first eight candidates (at <= 8 particles per cell: all of them) by cp.async
+                const float *src = reinterpret_cast<const float *>(a.spos + d.x + sub);
+                cp_async4(&sm.x[d.z + sub], src);
+                cp_async4(&sm.y[d.z + sub], src + 1);
+                cp_async4(&sm.z[d.z + sub], src + 2);
+                sm.slot[d.z + sub] = (uint16_t)(d.w + sub);
             }
+            // long segments: 16-byte loads, three in flight per lane (a 4-byte cp.async costs the L1 as many sectors as a
+            // 16-byte load, so the tail of a dense cell is cheaper through registers)
+            for (int q0 = sub + 8; q0 < d.y; q0 += 24) {
+                float4 w[3];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                if (sub < n[u]) {
-                    sm.x[f0[u] + sub] = v[u].x;
-                    sm.y[f0[u] + sub] = v[u].y;
-                    sm.z[f0[u] + sub] = v[u].z;
-                    sm.slot[f0[u] + sub] = (uint16_t)(slot0[u] + sub);
-                }
-            }
+                for (int k = 0; k < 3; ++k)
+                    if (q0 + 8 * k < d.y) w[k] = __ldg(&a.spos[d.x + q0 + 8 * k]);
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                for (int q0 = sub + 8; q0 < n[u]; q0 += 24) {
-                    float4 w[3];
-#pragma unroll
-                    for (int k = 0; k < 3; ++k)
-                        if (q0 + 8 * k < n[u]) w[k] = __ldg(&a.spos[gs[u] + q0 + 8 * k]);
-#pragma unroll
-                    for (int k = 0; k < 3; ++k) {
-                        const int q = q0 + 8 * k;
-                        if (q < n[u]) {
-                            sm.x[f0[u] + q] = w[k].x;
-                            sm.y[f0[u] + q] = w[k].y;
-                            sm.z[f0[u] + q] = w[k].z;
-                            sm.slot[f0[u] + q] = (uint16_t)(slot0[u] + q);
-                        }
+                for (int k = 0; k < 3; ++k) {
+                    const int q = q0 + 8 * k;
+                    if (q < d.y) {
+                        sm.x[d.z + q] = w[k].x;
+                        sm.y[d.z + q] = w[k].y;
+                        sm.z[d.z + q] = w[k].z;
+                        sm.slot[d.z + q] = (uint16_t)(d.w + q);
                     }
                 }
             }
+        };
+        for (int it = j >> 3; it < nseg; it += 2 * (FL_THREADS / 8)) {   // two descriptors per trip: one LDS.128 each
+            const int it1 = it + FL_THREADS / 8;
+            const int4 d0 = sm.u.st.seg[it];
+            const int4 d1 = (it1 < nseg) ? sm.u.st.seg[it1] : make_int4(0, 0, 0, 0);
+            stage_segment(d0);
+            stage_segment(d1);
         }
+        cp_async_wait_all();
     }
     // windows of the cells (block tables are final since the previous barrier)
     if (j < ncell) {

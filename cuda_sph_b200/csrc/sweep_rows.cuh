@@ -48,6 +48,7 @@ constexpr int RB_DENSITY_CTAS = RB_THREADS == 128 ? 4 : RB_THREADS == 64 ? 6 : 2
 #define SPH_RB_FORCE_CTAS (RB_THREADS == 128 ? 3 : RB_THREADS == 64 ? 4 : 2)
 #endif
 constexpr int RB_FORCE_CTAS = SPH_RB_FORCE_CTAS;
+constexpr int PF_AHEAD = 148 * 4;   // L2 prefetch distance of the sweeps, in tiles (about one wave of resident CTAs)
 constexpr int RB_KEEP = 33;       // superset candidates kept per particle (32 + spares for rejected band candidates)
 constexpr int RB_LSTRIDE = 38;    // uint16 per list row (19 words: conflict-free rows; >= RB_KEEP + 1)
 
@@ -67,6 +68,9 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+// L2 prefetch of a line another CTA will read soon (streaming inputs are cold in L2: the plans, lists and counts were
+// written before the 2 GB of lists pushed them out).  Out-of-range addresses are the caller's business.
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void mbar_inval(void *bar) {
     asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -712,6 +716,28 @@ __device__ __forceinline__ void force_rows_tile(const SweepArgs &a, const GridDe
     const uint8_t cf_raw = (j < nb) ? a.ncnt[t] : (uint8_t)0;
     const float rho_raw = (j < nb) ? a.srho[t] : 0.f;
     const uint32_t my_id = (j < nb) ? a.sids[t] : 0u;   // master slot of the epilogue's scatter
+    // the lists too: all four 16-byte pieces, whatever the count turns out to be (one round trip instead of two)
+    uint4 e[4];
+    {
+        const uint4 *lg = reinterpret_cast<const uint4 *>(a.nlist + (size_t)t * 32);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) e[q] = (j < nb) ? __ldg(&lg[q]) : make_uint4(0u, 0u, 0u, 0u);
+    }
+    if (only_pass == OWN_TILE) {   // streaming inputs of the tile that will run PF_AHEAD CTAs later -> L2
+        const int pt = tile + PF_AHEAD;
+        const int pp0 = pt * RB_THREADS;
+        if (pp0 + RB_THREADS <= a.n) {
+            if ((j >> 5) == 1) {
+                if (j == 32) prefetch_l2(&a.plans[pt]);
+                else if (j < 32 + 5) prefetch_l2(reinterpret_cast<const char *>(a.skeys + pp0) + (j - 33) * 128);
+                else if (j < 32 + 9) prefetch_l2(reinterpret_cast<const char *>(a.srho + pp0) + (j - 37) * 128);
+                else if (j < 32 + 13) prefetch_l2(reinterpret_cast<const char *>(a.sids + pp0) + (j - 41) * 128);
+                else if (j == 32 + 13) prefetch_l2(a.ncnt + pp0);
+            } else if ((j >> 5) >= 2) {   // 64 lines of lists
+                prefetch_l2(reinterpret_cast<const char *>(a.nlist + (size_t)pp0 * 32) + (j - 64) * 128);
+            }
+        }
+    }
     __syncthreads();   // mbarrier initialised, row_lo / row_base of a planned tile published
     // a fitting plan implies live particles; otherwise count them (a tile of dead particles stages nothing)
     const bool plan_fits = g.aligned && a.plans[tile].fits != 0 && a.plans[tile].slots > 0;
@@ -769,14 +795,6 @@ __device__ __forceinline__ void force_rows_tile(const SweepArgs &a, const GridDe
             }
             const bool in_pass = live && want && j >= j0 && j < j1;
             if (ok) {
-                // the lists travel while the rows land
-                uint4 e[4];
-                const uint4 *lg = reinterpret_cast<const uint4 *>(a.nlist + (size_t)t * 32);
-                if (in_pass && !walk) {
-#pragma unroll
-                    for (int q = 0; q < 4; ++q)
-                        if (q * 8 < my_cnt) e[q] = __ldg(&lg[q]);
-                }
                 while (!mbar_try_wait(&plan.mbar, parity)) {
                 }
                 parity ^= 1u;

@@ -21,6 +21,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import sys
 from typing import List, Optional, Sequence
 
 import numpy as np
@@ -525,8 +526,22 @@ class NativeSlabRunner:
             p2p = os.environ.get("SPH_SLAB_P2P", "1") != "0"
         self.p2p = False
         if p2p:
-            self._open_peers(col_hist, pipe_mode, dict(own_slack=own_slack, ghost_slack=ghost_slack,
-                                                       migrant_frac=migrant_frac, far_frac=far_frac), dev)
+            # every rank must end up on the same path: if CUDA IPC is unavailable on ANY rank (containers without a shared
+            # IPC namespace, peer access disabled) all ranks take the NCCL all_to_all path, loudly
+            err = None
+            try:
+                self._open_peers(col_hist, pipe_mode, dict(own_slack=own_slack, ghost_slack=ghost_slack,
+                                                           migrant_frac=migrant_frac, far_frac=far_frac), dev)
+            except Exception as exc:   # noqa: BLE001 -- reported below, then agreed on by all ranks
+                err = exc
+            ok = torch.tensor([0 if err else 1], device=dev, dtype=torch.int32)
+            if self.world > 1:
+                dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+            if int(ok.item()) == 0:
+                self.p2p = False
+                if err is not None or self.rank == 0:
+                    print(f"[slab rank {self.rank}] peer-memory exchange unavailable ({err}); using the NCCL all_to_all "
+                          "path on every rank", file=sys.stderr, flush=True)
 
         def view(which, shape, typestr, dtype):
             ptr, cnt = C.c_void_p(), C.c_int64()

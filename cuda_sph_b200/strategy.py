@@ -267,6 +267,12 @@ class B200SPHStrategy:
         _lib.check(self._lib.sph_get_stats(self._h, C.byref(s)))
         return {name: getattr(s, name) for name, _ in s._fields_}
 
+    def path_counters(self) -> dict:
+        """Work-item counts of the most recent step: which share of the tiles ran on which sweep path."""
+        out = np.zeros(4, np.int32)
+        _lib.check(self._lib.sph_path_counters(self._h, out.ctypes.data))
+        return dict(passes=int(out[0]), flat_refused=int(out[1]), dense_tiles=int(out[2]), tiles=int(out[3]))
+
     def launch_count(self) -> int:
         return int(self._lib.sph_launch_count(self._h))
 

@@ -186,6 +186,10 @@ int sph_get_rng_states(sph_handle_t h, uint64_t *states);        /* N x 2 uint64
 int sph_set_rng_states(sph_handle_t h, const uint64_t *states);
 int sph_get_stats(sph_handle_t h, SphStats *stats);
 int64_t sph_n_cells(sph_handle_t h);
+/* Diagnostics (no reference counterpart): work-item counts of the most recent step, out[4] = { 32-particle passes of
+ * tiles whose rows do not fit the staging, tiles handed over by density_flat_kernel, dense tiles (density_dense_kernel),
+ * number of 128-particle tiles }.  Says which share of a workload runs on which sweep path. */
+int sph_path_counters(sph_handle_t h, int32_t *out4);
 int sph_cell_dims(sph_handle_t h, int32_t *ceil3, int32_t *trunc3);
 
 /* ---- frame export pipeline (section 8(f)1).  Replaces the per-frame __finalize_computation + np.save sequence of
