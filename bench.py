@@ -54,9 +54,9 @@ BYTES = {"hash": 20, "reorder": 72, "density": 20, "force": 84}   # B / particle
 
 
 def sort_bytes(passes: int) -> int:
-    # onesweep: one histogram pass reads the keys (4); every digit pass reads key + value (8) and writes key + value
-    # (8); pass 0 has no value read (values are iota)
-    return 4 + passes * 16 - 4
+    # onesweep: every digit pass reads key + value (8) and writes key + value (8); pass 0 has no value read (values are
+    # iota); the digit histograms come from hash_hist_kernel (counted under "hash": it reads the positions, not the keys)
+    return passes * 16 - 4
 
 
 def make_workload(name: str, n_override: int | None):

@@ -64,11 +64,24 @@ hash_hist_kernel(const float4 *__restrict__ pos_m, uint32_t *__restrict__ keys, 
     const int tid = threadIdx.x;
     for (int p = 0; p < ps.n_passes; ++p) hist[p][tid] = 0;
     __syncthreads();
-    for (int i = blockIdx.x * OS_THREADS + tid; i < n; i += gridDim.x * OS_THREADS) {
-        const float4 q = pos_m[i];
-        const uint32_t k = key_of(g, q.x, q.y, q.z);
-        keys[i] = k;
-        for (int p = 0; p < ps.n_passes; ++p) atomicAdd(&hist[p][(k >> ps.shift[p]) & ps.mask[p]], 1u);
+    // four independent position loads in flight per thread (the fp64 division of key_of sits behind each of them)
+    const int stride = gridDim.x * OS_THREADS;
+    for (int i0 = blockIdx.x * OS_THREADS + tid; i0 < n; i0 += 4 * stride) {
+        float4 q[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * stride;
+            if (i < n) q[u] = pos_m[MI(i)];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * stride;
+            if (i < n) {
+                const uint32_t k = key_of(g, q[u].x, q[u].y, q[u].z);
+                keys[i] = k;
+                for (int p = 0; p < ps.n_passes; ++p) atomicAdd(&hist[p][(k >> ps.shift[p]) & ps.mask[p]], 1u);
+            }
+        }
     }
     __syncthreads();
     for (int p = 0; p < ps.n_passes; ++p) {
@@ -313,8 +326,12 @@ ts_scatter(const uint32_t *__restrict__ kin, const uint32_t *__restrict__ vin, u
 constexpr int OS2_ITEMS = 16;
 constexpr int OS2_TILE = OS_THREADS * OS2_ITEMS;   // 4096 pairs per tile
 
+constexpr int OS2_RUNS = 2 * OS_WARPS;
+
 struct Os2Smem {
-    uint32_t wcnt[OS_WARPS][OS_RADIX];   // per-warp digit counts, then the warp's first local position of a digit
+    // digit counts per HALF warp-tile (a warp's 512 pairs are ranked as two runs of 256 with their own counters, so two
+    // independent match / count / update chains are in flight per thread), then the run's first local position of a digit
+    uint32_t wcnt[OS2_RUNS][OS_RADIX];
     uint32_t delta[OS_RADIX];            // global position of a pair = delta[digit] + its position in the sorted tile
     uint32_t skey[OS2_TILE], sval[OS2_TILE];
     uint32_t warp_sum[OS_WARPS], warp_sum2[OS_WARPS];
@@ -348,7 +365,7 @@ os2_pass(const uint32_t *__restrict__ kin, const uint32_t *__restrict__ vin, uin
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (LOOKBACK && tid == 0) sm.tile = (int)atomicAdd(&ctrl[n_passes * OS_RADIX + pass], 1u);
 #pragma unroll
-    for (int w = 0; w < OS_WARPS; ++w) sm.wcnt[w][tid] = 0;
+    for (int w = 0; w < OS2_RUNS; ++w) sm.wcnt[w][tid] = 0;
     __syncthreads();
     const int tile = LOOKBACK ? sm.tile : (int)blockIdx.x;
     const int nvalid = min(OS2_TILE, n - tile * OS2_TILE);
@@ -368,25 +385,28 @@ os2_pass(const uint32_t *__restrict__ kin, const uint32_t *__restrict__ vin, uin
         val[k] = (i < n) ? (vin ? vin[i] : (uint32_t)i) : 0u;
     }
 #pragma unroll
-    for (int k = 0; k < OS2_ITEMS; ++k) {
-        const int i = wbase + k * 32 + lane;
-        const bool valid = i < n;
-        const uint32_t d = (key[k] >> shift) & mask;
-        const uint32_t peers = __match_any_sync(0xffffffffu, valid ? d : (0x10000u + lane));
-        uint32_t pre = 0;
-        if (valid) pre = sm.wcnt[warp][d];
+    for (int k = 0; k < OS2_ITEMS / 2; ++k) {   // items k (first run) and k + 8 (second run) together
+        const int ia = wbase + k * 32 + lane, ib = ia + (OS2_ITEMS / 2) * 32;
+        const bool va = ia < n, vb = ib < n;
+        const uint32_t da = (key[k] >> shift) & mask, db = (key[k + OS2_ITEMS / 2] >> shift) & mask;
+        const uint32_t pa = __match_any_sync(0xffffffffu, va ? da : (0x10000u + lane));
+        const uint32_t pb = __match_any_sync(0xffffffffu, vb ? db : (0x10000u + lane));
+        uint32_t prea = 0, preb = 0;
+        if (va) prea = sm.wcnt[2 * warp][da];
+        if (vb) preb = sm.wcnt[2 * warp + 1][db];
         __syncwarp();
-        if (valid && (peers & lt) == 0) sm.wcnt[warp][d] = pre + __popc(peers);
+        if (va && (pa & lt) == 0) sm.wcnt[2 * warp][da] = prea + __popc(pa);
+        if (vb && (pb & lt) == 0) sm.wcnt[2 * warp + 1][db] = preb + __popc(pb);
         __syncwarp();
-        const uint32_t r = pre + __popc(peers & lt);
-        rank2[k >> 1] = (k & 1) ? (rank2[k >> 1] | (r << 16)) : r;
+        const uint32_t ra = prea + __popc(pa & lt), rb = preb + __popc(pb & lt);
+        rank2[k] = ra | (rb << 16);   // low half: item k, high half: item k + 8
     }
     __syncthreads();
 
     // digit `tid`: count in this tile, start inside the sorted tile, global offset
     uint32_t tile_cnt = 0;
 #pragma unroll
-    for (int w = 0; w < OS_WARPS; ++w) tile_cnt += sm.wcnt[w][tid];
+    for (int w = 0; w < OS2_RUNS; ++w) tile_cnt += sm.wcnt[w][tid];
     uint32_t gbase;   // global position of the tile's first pair of digit `tid`
     if (LOOKBACK) {
         volatile uint32_t *status = ctrl + (size_t)n_passes * OS_RADIX + 8 + ((size_t)pass * ntiles) * OS_RADIX;
@@ -435,9 +455,9 @@ os2_pass(const uint32_t *__restrict__ kin, const uint32_t *__restrict__ vin, uin
         }
     }
     sm.delta[tid] = gbase - lstart;
-    uint32_t running = lstart;   // per-warp first positions (warp order == input order)
+    uint32_t running = lstart;   // per-run first positions (run order == input order)
 #pragma unroll
-    for (int w = 0; w < OS_WARPS; ++w) {
+    for (int w = 0; w < OS2_RUNS; ++w) {
         const uint32_t c = sm.wcnt[w][tid];
         sm.wcnt[w][tid] = running;
         running += c;
@@ -448,7 +468,8 @@ os2_pass(const uint32_t *__restrict__ kin, const uint32_t *__restrict__ vin, uin
         const int i = wbase + k * 32 + lane;
         if (i < n) {
             const uint32_t d = (key[k] >> shift) & mask;
-            const uint32_t p = sm.wcnt[warp][d] + ((rank2[k >> 1] >> ((k & 1) * 16)) & 0xffffu);
+            const int h = k / (OS2_ITEMS / 2), kk = k % (OS2_ITEMS / 2);
+            const uint32_t p = sm.wcnt[2 * warp + h][d] + ((rank2[kk] >> (h * 16)) & 0xffffu);
             sm.skey[p] = key[k];
             sm.sval[p] = val[k];
         }

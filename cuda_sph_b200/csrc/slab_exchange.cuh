@@ -104,8 +104,8 @@ slab_route_kernel(SlabRoute r, float4 *__restrict__ pos_m, const float4 *__restr
     float4 p = make_float4(0.f, 0.f, 0.f, 0.f), v = p;
     int col = -1, o = r.rank;
     if (have) {
-        p = pos_m[i];
-        v = vel_m[i];
+        p = pos_m[MI(i)];
+        v = vel_m[MI(i)];
         col = slab_column(p.x, r.voxel_x);
         if (col >= 0) o = slab_owner(r, col);   // a particle without a column (non-finite x) stays where it is, dead
     }
@@ -118,7 +118,7 @@ slab_route_kernel(SlabRoute r, float4 *__restrict__ pos_m, const float4 *__restr
     slab_emit(r, sendbuf, counters, ghost_r, o + 1, 1, p, v, g, nullptr);
     if (leaves) {   // the slot becomes a hole
         gid[i] = -1;
-        pos_m[i] = make_float4(__int_as_float(0x7fc00000), 0.f, 0.f, 0.f);
+        pos_m[MI(i)] = make_float4(__int_as_float(0x7fc00000), 0.f, 0.f, 0.f);
     }
 }
 
@@ -160,7 +160,7 @@ slab_route_cta_kernel(const __grid_constant__ SlabEmit em, float4 *__restrict__ 
     const int g = (i < r.own_cap) ? gid[i] : -1;
     const bool have = g >= 0;
     float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (have) p = pos_m[i];
+    if (have) p = pos_m[MI(i)];
     // most particles sit in the interior of the slab: decide that without the fp64 division (the fp32 estimate of
     // x / voxel is off by < 1e-3 for |q| < 4096; whoever is near a column boundary takes the exact path)
     const float q = p.x * em.inv_vx, fl = floorf(q), fr = q - fl;
@@ -200,7 +200,7 @@ slab_route_cta_kernel(const __grid_constant__ SlabEmit em, float4 *__restrict__ 
         s_base[threadIdx.x] = atomicAdd(&em.cnt[threadIdx.x], s_cnt[threadIdx.x]);
     __syncthreads();
     if (rec[0] || rec[1] || rec[2]) {
-        const float4 v = vel_m[i];
+        const float4 v = vel_m[MI(i)];
 #pragma unroll
         for (int u = 0; u < 3; ++u) {
             if (!rec[u]) continue;
@@ -226,7 +226,7 @@ slab_route_cta_kernel(const __grid_constant__ SlabEmit em, float4 *__restrict__ 
         }
         if (rec[0]) {   // the slot becomes a hole
             gid[i] = -1;
-            pos_m[i] = make_float4(__int_as_float(0x7fc00000), 0.f, 0.f, 0.f);
+            pos_m[MI(i)] = make_float4(__int_as_float(0x7fc00000), 0.f, 0.f, 0.f);
         }
     }
 }
@@ -283,7 +283,7 @@ slab_clear_ghosts_kernel(SlabRoute r, float4 *__restrict__ pos_m, int32_t *__res
     if (i >= r.capacity) return;
     if (gid[i] >= 0) {
         gid[i] = -1;
-        pos_m[i] = make_float4(__int_as_float(0x7fc00000), 0.f, 0.f, 0.f);
+        pos_m[MI(i)] = make_float4(__int_as_float(0x7fc00000), 0.f, 0.f, 0.f);
     }
 }
 
@@ -332,8 +332,8 @@ slab_unpack_kernel(SlabRoute r, const unsigned char *__restrict__ recvbuf, float
     const float4 p = *reinterpret_cast<const float4 *>(rec);
     const float4 v = *reinterpret_cast<const float4 *>(rec + 16);
     const int g = __float_as_int(v.w);
-    pos_m[dst] = p;
-    vel_m[dst] = make_float4(v.x, v.y, v.z, 0.f);
+    pos_m[MI(dst)] = p;
+    vel_m[MI(dst)] = make_float4(v.x, v.y, v.z, 0.f);
     gid[dst] = g;
     if (migrant && r.rec_bytes == 48 && rng) {
         const ulonglong2 s = *reinterpret_cast<const ulonglong2 *>(rec + 32);
@@ -365,8 +365,8 @@ slab_compact_gather_kernel(SlabRoute r, const float4 *__restrict__ pos_m, const 
     base = __shfl_sync(0xffffffffu, base, 0);
     if (!have) return;
     const int dst = base + __popc(m & ((1u << lane) - 1u));
-    tpos[dst] = pos_m[i];
-    tvel[dst] = vel_m[i];
+    tpos[dst] = pos_m[MI(i)];
+    tvel[dst] = vel_m[MI(i)];
     tgid[dst] = gid[i];
 }
 
@@ -380,12 +380,12 @@ slab_compact_scatter_kernel(SlabRoute r, float4 *__restrict__ pos_m, float4 *__r
     if (i >= r.own_cap) return;
     const int n = counters[SLAB_SCRATCH];
     if (i < n) {
-        pos_m[i] = tpos[i];
-        vel_m[i] = tvel[i];
+        pos_m[MI(i)] = tpos[i];
+        vel_m[MI(i)] = tvel[i];
         gid[i] = tgid[i];
     } else {
         gid[i] = -1;
-        pos_m[i] = make_float4(__int_as_float(0x7fc00000), 0.f, 0.f, 0.f);
+        pos_m[MI(i)] = make_float4(__int_as_float(0x7fc00000), 0.f, 0.f, 0.f);
     }
 }
 

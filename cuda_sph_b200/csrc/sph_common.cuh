@@ -7,6 +7,10 @@ namespace sph {
 
 constexpr int kMaxNeighbours = 32;  // MAX_NEIGHBOURS, reference config.py:30
 
+// Index of particle i in the master arrays: one 32-byte record (position | velocity) per particle, pos_m and
+// vel_m = pos_m + 1 both step by two float4 (layout note in sph_kernels.cuh).
+__host__ __device__ __forceinline__ size_t MI(size_t i) { return 2 * i; }
+
 // Uniform grid.  Keys are linearised with the CEIL dims (voxel_sph_strategy.py:70-73) while the neighbour walk bounds
 // and linearises with the TRUNC dims (voxel_sph_strategy.py:110-116, voxel_kernels.py:56,60) -- reference quirk Q2,
 // reproduced literally.  xoff shifts the x cell coordinate for slab-local tables (0 on a single GPU).

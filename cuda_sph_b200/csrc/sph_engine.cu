@@ -306,8 +306,8 @@ int sph_create(const SphParams *params, int device, sph_handle_t *out) {
             return 1;                                                                       \
         }                                                                                   \
     } while (0)
-    ALLOC(e->pos_m, n);
-    ALLOC(e->vel_m, n);
+    ALLOC(e->pos_m, 2 * (size_t)n);   // 32-byte records: position | velocity (sph_kernels.cuh)
+    e->vel_m = e->pos_m + 1;
     ALLOC(e->spos, n);
     ALLOC(e->svel, n);
     ALLOC(e->sforce, n);
@@ -357,8 +357,7 @@ int sph_create(const SphParams *params, int device, sph_handle_t *out) {
     e->skeys = final_in_a ? e->ka : e->kb;
     e->sids = final_in_a ? e->va : e->vb;
 
-    cudaMemset(e->pos_m, 0, sizeof(float4) * (size_t)n);
-    cudaMemset(e->vel_m, 0, sizeof(float4) * (size_t)n);
+    cudaMemset(e->pos_m, 0, 2 * sizeof(float4) * (size_t)n);
     cudaMemset(e->sforce, 0, sizeof(float4) * (size_t)n);
     cudaMemset(e->srho, 0, sizeof(float) * (size_t)n);
     cudaMemset(e->keys, 0, sizeof(uint32_t) * (size_t)n);
@@ -411,7 +410,7 @@ int sph_destroy(sph_handle_t e) {
     cudaSetDevice(e->device);
     cudaDeviceSynchronize();
     invalidate_graph(e);
-    void *ptrs[] = {e->pos_m, e->vel_m, e->spos, e->svel, e->sforce, e->spress, e->svisc, e->srho, e->nlist, e->dlist, e->ncnt,
+    void *ptrs[] = {e->pos_m, e->spos, e->svel, e->sforce, e->spress, e->svisc, e->srho, e->nlist, e->dlist, e->ncnt,
                     e->keys, e->ka, e->va, e->kb, e->vb, e->block_hist, e->digit_total, e->os_ctrl, e->tile_plans, e->refused, e->cell_range, e->pipe_d,
                     e->rng, e->gid, e->stage, e->stats_d, e->snap_pos, e->snap_vel, e->snap_rng, e->sendbuf, e->recv_alloc, e->emit_d, e->peer_flags_d, e->emit_cnt,
                     e->slab_counters, e->tmp_gid};
@@ -974,8 +973,7 @@ int sph_save_state(sph_handle_t e) {
     if (!e->has_state) return fail("no particle state to save");
     CK(cudaSetDevice(e->device));
     const size_t n = e->n;
-    if (!e->snap_pos) CK(cudaMalloc((void **)&e->snap_pos, sizeof(float4) * n));
-    if (!e->snap_vel) CK(cudaMalloc((void **)&e->snap_vel, sizeof(float4) * n));
+    if (!e->snap_pos) CK(cudaMalloc((void **)&e->snap_pos, 2 * sizeof(float4) * n));   // whole records (position | velocity)
     const size_t rng_bytes = 2 * sizeof(uint64_t) * (size_t)e->rng_count;   // slab mode: one state per GLOBAL particle
     if (e->rng && e->snap_rng && e->snap_rng_count != e->rng_count) {
         cudaFree(e->snap_rng);
@@ -985,8 +983,7 @@ int sph_save_state(sph_handle_t e) {
         CK(cudaMalloc((void **)&e->snap_rng, rng_bytes));
         e->snap_rng_count = e->rng_count;
     }
-    CK(cudaMemcpyAsync(e->snap_pos, e->pos_m, sizeof(float4) * n, cudaMemcpyDeviceToDevice, e->stream));
-    CK(cudaMemcpyAsync(e->snap_vel, e->vel_m, sizeof(float4) * n, cudaMemcpyDeviceToDevice, e->stream));
+    CK(cudaMemcpyAsync(e->snap_pos, e->pos_m, 2 * sizeof(float4) * n, cudaMemcpyDeviceToDevice, e->stream));
     if (e->rng) CK(cudaMemcpyAsync(e->snap_rng, e->rng, rng_bytes, cudaMemcpyDeviceToDevice, e->stream));
     e->snap_steps = e->steps_done;
     return 0;
@@ -997,8 +994,7 @@ int sph_restore_state(sph_handle_t e) {
     if (e->snap_steps < 0) return fail("sph_save_state has not been called");
     CK(cudaSetDevice(e->device));
     const size_t n = e->n;
-    CK(cudaMemcpyAsync(e->pos_m, e->snap_pos, sizeof(float4) * n, cudaMemcpyDeviceToDevice, e->stream));
-    CK(cudaMemcpyAsync(e->vel_m, e->snap_vel, sizeof(float4) * n, cudaMemcpyDeviceToDevice, e->stream));
+    CK(cudaMemcpyAsync(e->pos_m, e->snap_pos, 2 * sizeof(float4) * n, cudaMemcpyDeviceToDevice, e->stream));
     if (e->rng && e->snap_rng && e->snap_rng_count == e->rng_count)
         CK(cudaMemcpyAsync(e->rng, e->snap_rng, 2 * sizeof(uint64_t) * (size_t)e->rng_count, cudaMemcpyDeviceToDevice,
                            e->stream));
@@ -1100,7 +1096,7 @@ int sph_slab_exchange_init(sph_handle_t e, int32_t world, int32_t rank, const in
     CK(cudaMemset(e->slab_counters, 0, 8 * sizeof(int32_t)));
     // every slot starts empty
     CK(cudaMemset(e->gid, 0xff, sizeof(int32_t) * (size_t)e->n));
-    CK(cudaMemset(e->pos_m, 0xff, sizeof(float4) * (size_t)e->n));
+    CK(cudaMemset2D(e->pos_m, 2 * sizeof(float4), 0xff, sizeof(float4), (size_t)e->n));   // positions only (record stride)
     if (sendbuf) *sendbuf = e->sendbuf;
     if (recvbuf) *recvbuf = e->recvbuf;
     e->route_ready = true;

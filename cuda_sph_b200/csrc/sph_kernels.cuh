@@ -2,7 +2,10 @@
 // the fp64 <-> fp32 state converters at the host boundary and the parity-tap helpers.
 //
 // Data layout in HBM:
-//   master  pos_m[N] float4 (x, y, z, density), vel_m[N] float4 (vx, vy, vz, 0)      -- particle-id order
+//   master  one 32-byte record per particle, particle-id order: float4 (x, y, z, density) | float4 (vx, vy, vz, 0).
+//           pos_m points at record 0, vel_m = pos_m + 1, and particle i is pos_m[MI(i)] / vel_m[MI(i)] (MI(i) = 2 i):
+//           the random gather of the reorder and the random scatter of the force epilogue then touch ONE 32-byte sector
+//           per particle (two arrays cost two sectors = two 64-byte DRAM atoms: ncu, reorder_kernel at 77 % DRAM)
 //   sorted  spos[N]  float4 (x, y, z, -),       svel[N]  float4, srho[N] float        -- cell-contiguous order
 //   cells   cell_range[ncells + 1] int2 (begin, end) into the sorted arrays; entry ncells is the dead cell
 #pragma once
@@ -16,7 +19,7 @@ __global__ void __launch_bounds__(256)
 hash_kernel(const float4 *__restrict__ pos_m, uint32_t *__restrict__ keys, int n, GridDesc g) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const float4 p = pos_m[i];
+    const float4 p = pos_m[MI(i)];
     keys[i] = key_of(g, p.x, p.y, p.z);
 }
 
@@ -42,8 +45,8 @@ reorder_kernel(const uint32_t *__restrict__ skeys, const uint32_t *__restrict__ 
         }
     }
     if (t == n - 1) cell_range[key].y = n;
-    spos[t] = pos_m[id];
-    if (WITH_VEL) svel[t] = vel_m[id];
+    spos[t] = pos_m[MI(id)];
+    if (WITH_VEL) svel[t] = vel_m[MI(id)];
 }
 
 // Velocity half of the reorder, for callers whose velocities arrive late (sph_compute_next_state uploads them while the
@@ -52,7 +55,7 @@ __global__ void __launch_bounds__(256)
 gather_vel_kernel(const uint32_t *__restrict__ sids, const float4 *__restrict__ vel_m, float4 *__restrict__ svel, int n) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
-    const float4 v = vel_m[sids[t]];
+    const float4 v = vel_m[MI(sids[t])];
     float *o = reinterpret_cast<float *>(svel + t);
     o[0] = v.x;
     o[1] = v.y;
@@ -105,19 +108,19 @@ pack_state_kernel(const T *__restrict__ pos3, const T *__restrict__ vel3, float4
                   float4 *__restrict__ vel_m, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    pos_m[i] = make_float4((float)pos3[3 * (size_t)i], (float)pos3[3 * (size_t)i + 1], (float)pos3[3 * (size_t)i + 2],
+    pos_m[MI(i)] = make_float4((float)pos3[3 * (size_t)i], (float)pos3[3 * (size_t)i + 1], (float)pos3[3 * (size_t)i + 2],
                            0.f);
-    vel_m[i] = make_float4((float)vel3[3 * (size_t)i], (float)vel3[3 * (size_t)i + 1], (float)vel3[3 * (size_t)i + 2],
+    vel_m[MI(i)] = make_float4((float)vel3[3 * (size_t)i], (float)vel3[3 * (size_t)i + 1], (float)vel3[3 * (size_t)i + 2],
                            0.f);
 }
 
 // one (N,3) host-layout array -> float4 (w = 0)
 template <typename T>
 __global__ void __launch_bounds__(256)
-pack_vec_kernel(const T *__restrict__ src3, float4 *__restrict__ dst, int n) {
+pack_vec_kernel(const T *__restrict__ src3, float4 *__restrict__ dst, int n) {   // dst: pos_m or vel_m (record stride)
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    dst[i] = make_float4((float)src3[3 * (size_t)i], (float)src3[3 * (size_t)i + 1], (float)src3[3 * (size_t)i + 2], 0.f);
+    dst[MI(i)] = make_float4((float)src3[3 * (size_t)i], (float)src3[3 * (size_t)i + 1], (float)src3[3 * (size_t)i + 2], 0.f);
 }
 
 // sorted fp32 scalar (density) -> id-ordered fp64
@@ -134,7 +137,7 @@ unpack_state_kernel(const float4 *__restrict__ pos_m, const float4 *__restrict__
                     T *__restrict__ vel3, T *__restrict__ rho, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const float4 p = pos_m[i], v = vel_m[i];
+    const float4 p = pos_m[MI(i)], v = vel_m[MI(i)];
     if (pos3) {
         pos3[3 * (size_t)i] = (T)p.x;
         pos3[3 * (size_t)i + 1] = (T)p.y;
@@ -185,7 +188,7 @@ stats_kernel(const float4 *__restrict__ pos_m, const float4 *__restrict__ vel_m,
     uint32_t bad = 0;
     float rho = 0.f, sp = 0.f;
     if (i < n) {
-        const float4 p = pos_m[i], v = vel_m[i];
+        const float4 p = pos_m[MI(i)], v = vel_m[MI(i)];
         const bool fin = isfinite(p.x) && isfinite(p.y) && isfinite(p.z) && isfinite(v.x) && isfinite(v.y) &&
                          isfinite(v.z);
         bad = fin ? 0u : 1u;
@@ -212,7 +215,7 @@ export_pack_kernel(const float4 *__restrict__ pos_m, const float4 *__restrict__ 
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n_out) return;
     const size_t i = (size_t)k * stride;
-    const float4 p = pos_m[i], v = vel_m[i];
+    const float4 p = pos_m[MI(i)], v = vel_m[MI(i)];
     double *pos3 = out, *vel3 = out + 3 * (size_t)n_out, *rho = out + 6 * (size_t)n_out;
     pos3[3 * (size_t)k] = p.x;
     pos3[3 * (size_t)k + 1] = p.y;
@@ -279,8 +282,8 @@ generate_kernel(float4 *__restrict__ pos_m, float4 *__restrict__ vel_m, int n, G
         y = (float)__dadd_rn(ga.pipe[1], __dmul_rn(a, rmax));
         z = (float)__dadd_rn(ga.pipe[2], __dmul_rn(b, rmax));
     }
-    pos_m[i] = make_float4(x, y, z, 0.f);
-    vel_m[i] = make_float4(vx, vy, vz, 0.f);
+    pos_m[MI(i)] = make_float4(x, y, z, 0.f);
+    vel_m[MI(i)] = make_float4(vx, vy, vz, 0.f);
 }
 
 // ---- per-frame reductions (section 8(f)4; analize.py:9-14) ----------------------------------------------------------
@@ -307,7 +310,7 @@ frame_stats_kernel(const float4 *__restrict__ pos_m, const float4 *__restrict__ 
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t bad = 0, pmax = 0, pmin = 0xffffffffu, vmax = 0, smax = 0, dmax = 0;
     if (i < n) {
-        const float4 p = pos_m[i], v = vel_m[i];
+        const float4 p = pos_m[MI(i)], v = vel_m[MI(i)];
         const bool fin = isfinite(p.x) && isfinite(p.y) && isfinite(p.z) && isfinite(v.x) && isfinite(v.y) &&
                          isfinite(v.z);
         bad = fin ? 0u : 1u;

@@ -145,9 +145,12 @@ struct ForceAcc {
 // integrating_kernel + collision kernel in fp64 (base_kernels.py:30-98), scatter to the id-ordered master arrays.
 template <bool RECORD_TERMS>
 __device__ __forceinline__ void finish_particle(const SweepArgs &a, const StepConsts &c, int t, const float4 pi,
-                                                const float4 vi, float rho_i, ForceAcc f, uint32_t id) {
+                                                const float4 vi, float rho_i, ForceAcc f, uint32_t id,
+                                                bool maybe_empty = true) {
     if ((int)id >= a.n_own) return;              // ghost particle of an x-slab: its owner integrates it
-    if (a.gid && a.gid[id] < 0) return;          // empty slot of an x-slab (hole left by an emigrant / unused capacity)
+    // empty slot of an x-slab (hole left by an emigrant / unused capacity): x = NaN, so only a DEAD particle can be one --
+    // callers that know their particle is alive skip this random 4-byte gather
+    if (maybe_empty && a.gid && a.gid[id] < 0) return;
     if (f.any) {  // with no neighbour besides self the reference's sums stay exactly 0 (and rho_i is 0)
         const float s = c.mass_visc / rho_i;
         f.ux *= s;
@@ -174,8 +177,8 @@ __device__ __forceinline__ void finish_particle(const SweepArgs &a, const StepCo
     } else {
         collide_box(x, v, c);
     }
-    a.pos_m[id] = make_float4((float)x[0], (float)x[1], (float)x[2], rho_i);
-    a.vel_m[id] = make_float4((float)v[0], (float)v[1], (float)v[2], 0.f);
+    a.pos_m[MI(id)] = make_float4((float)x[0], (float)x[1], (float)x[2], rho_i);
+    a.vel_m[MI(id)] = make_float4((float)v[0], (float)v[1], (float)v[2], 0.f);
     a.sforce[t] = make_float4((float)F[0], (float)F[1], (float)F[2], 0.f);
     if (RECORD_TERMS) {
         a.spress[t] = make_float4(f.px, f.py, f.pz, 0.f);

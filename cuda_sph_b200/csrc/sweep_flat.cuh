@@ -316,16 +316,19 @@ density_flat_kernel(const SweepArgs a, const GridDesc g, const StepConsts c, con
     {
         const int sub = lane & 7;
         auto stage_segment = [&](const int4 d) {   // (first sorted index, length, staged position, first row slot)
-            if (sub < d.y) {   // the first eight candidates (at <= 8 particles per cell: all of them) by cp.async
-                const float *src = reinterpret_cast<const float *>(a.spos + d.x + sub);
-                cp_async4(&sm.x[d.z + sub], src);
-                cp_async4(&sm.y[d.z + sub], src + 1);
-                cp_async4(&sm.z[d.z + sub], src + 2);
-                sm.slot[d.z + sub] = (uint16_t)(d.w + sub);
+            // short segments (<= 16 candidates: everything at <= 8 particles per cell) entirely by cp.async, of long ones
+            // the first eight
+            const int na = d.y <= 16 ? d.y : 8;
+            for (int q = sub; q < na; q += 8) {
+                const float *src = reinterpret_cast<const float *>(a.spos + d.x + q);
+                cp_async4(&sm.x[d.z + q], src);
+                cp_async4(&sm.y[d.z + q], src + 1);
+                cp_async4(&sm.z[d.z + q], src + 2);
+                sm.slot[d.z + q] = (uint16_t)(d.w + q);
             }
-            // long segments: 16-byte loads, three in flight per lane (a 4-byte cp.async costs the L1 as many sectors as a
-            // 16-byte load, so the tail of a dense cell is cheaper through registers)
-            for (int q0 = sub + 8; q0 < d.y; q0 += 24) {
+            // the tail of long segments: 16-byte loads, three in flight per lane (a 4-byte cp.async costs the L1 as many
+            // sectors as a 16-byte load, so a dense cell is cheaper through registers)
+            for (int q0 = sub + na; q0 < d.y; q0 += 24) {
                 float4 w[3];
 #pragma unroll
                 for (int k = 0; k < 3; ++k)

@@ -777,6 +777,7 @@ __device__ __forceinline__ void force_rows_tile(const SweepArgs &a, const GridDe
         float4 pi = make_float4(0.f, 0.f, 0.f, 0.f), vi = pi;
         float rho_f = rho_i;
         bool fin = false, need_walk = false;
+        const bool was_dead = dead_todo;
         if (dead_todo) {
             pi = a.spos[t];
             vi = a.svel[t];
@@ -834,7 +835,7 @@ __device__ __forceinline__ void force_rows_tile(const SweepArgs &a, const GridDe
             f = fw;
             fin = true;
         }
-        if (fin) finish_particle<RECORD>(a, c, t, pi, vi, rho_f, f, my_id);
+        if (fin) finish_particle<RECORD>(a, c, t, pi, vi, rho_f, f, my_id, was_dead);
 
         if (pass >= RB_WARPS || (pass < 0 && tp_fits) || only_pass >= 0) break;
         ++pass;

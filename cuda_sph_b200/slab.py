@@ -371,8 +371,9 @@ class GpuSlabRunner(SlabRunner):
             self._chk(self._lib.sph_device_ptr(self._h, which, C.byref(ptr), C.byref(cnt)))
             return torch.as_tensor(_CudaBuffer(ptr.value, shape, typestr), device=dev).view(dtype)
 
-        self.P = view(0, (cap, 4), "<f4", torch.float32)
-        self.V = view(1, (cap, 4), "<f4", torch.float32)
+        # master arrays: one 32-byte record (position float4 | velocity float4) per slot -> two strided views of it
+        M = view(0, (cap, 8), "<f4", torch.float32)
+        self.P, self.V = M[:, 0:4], M[:, 4:8]
         self.G = view(4, (cap,), "<i4", torch.int32)
         self.R = view(5, (self.n_global, 2), "<i8", torch.int64) if p.mode == _lib.MODE_PIPE else None
 
@@ -549,8 +550,9 @@ class NativeSlabRunner:
             return torch.as_tensor(_CudaBuffer(ptr.value, shape, typestr), device=dev).view(dtype)
 
         cap = self.capacity
-        self.P = view(0, (cap, 4), "<f4", torch.float32)
-        self.V = view(1, (cap, 4), "<f4", torch.float32)
+        # master arrays: one 32-byte record (position float4 | velocity float4) per slot -> two strided views of it
+        M = view(0, (cap, 8), "<f4", torch.float32)
+        self.P, self.V = M[:, 0:4], M[:, 4:8]
         self.G = view(4, (cap,), "<i4", torch.int32)
         self.counters = view(6, (8,), "<i4", torch.int32)
         self.R = view(5, (self.n_global, 2), "<i8", torch.int64) if pipe_mode else None   # xoroshiro128+ states by global id

@@ -88,7 +88,12 @@ class B200SPHStrategy:
 
     # ------------------------------------------------------------------ reference-facing call
     def compute_next_state(self, old_state: SimulationState) -> SimulationState:
-        """abstract_sph_strategy.py:31-46: one step, host arrays in, fresh host arrays out."""
+        """abstract_sph_strategy.py:31-46: one step, host arrays in, fresh host arrays out.
+
+        Precision: the engine computes in fp32 and rounds the fp64 input once, on the way in, so the result is the
+        reference's result on float32(old_state) -- bit-exact grid / sort / neighbour lists, physics within 1e-4
+        (INTEGRATION.md "Input precision"; a state that is not fp32-representable may differ from the reference run on
+        the fp64 values where the rounding moves a particle across a cell face or a pair across r = h)."""
         self.old_state = old_state
         n = self.n
         pos = _f64(old_state.position, (n, 3))

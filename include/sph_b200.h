@@ -231,8 +231,9 @@ typedef struct SphFrameStats {
 int sph_get_frame_stats(sph_handle_t h, SphFrameStats *stats);               /* current state; synchronises */
 int sph_export_stats(sph_handle_t h, int32_t slot, SphFrameStats *stats);    /* of the frame exported into `slot` */
 
-/* Device pointers for zero-copy wrapping (torch / __cuda_array_interface__).  which: 0 = master position float4[N]
- * (x,y,z,density), 1 = master velocity float4[N], 2 = sorted ids int32[N], 3 = sorted position float4[N],
+/* Device pointers for zero-copy wrapping (torch / __cuda_array_interface__).  which: 0 = master records, 32 bytes per
+ * particle in id order: float4 (x,y,z,density) | float4 (vx,vy,vz,0), i.e. float[N][8]; 1 = the velocity half of
+ * record 0 (= pointer 0 + 16 bytes, same 32-byte stride); 2 = sorted ids int32[N], 3 = sorted position float4[N],
  * 4 = global ids int32[capacity] (x-slab mode), 5 = xoroshiro states uint64[2 * count] (PIPE mode),
  * 6 = slab counters int32[8] (native exchange: high-water mark, ghosts, overflow, scratch, live). */
 int sph_device_ptr(sph_handle_t h, int32_t which, void **ptr, int64_t *n_elements);
