@@ -321,7 +321,7 @@ ts_scatter(const uint32_t *__restrict__ kin, const uint32_t *__restrict__ vin, u
 // is first sorted by its digit INSIDE shared memory (stable: position = digit start in the tile + pairs of the earlier
 // warps + rank inside the warp), then written out in that order, so that consecutive threads write consecutive
 // addresses of a digit's run (16 pairs = 64 B on average at 4096-pair tiles and 256 digits).  Ranks come from
-// match.any (one instruction instead of eight ballots).  LOOKBACK selects how a tile learns its global offsets:
+// eight ballots per key (two keys in flight per thread).  LOOKBACK selects how a tile learns its global offsets:
 // decoupled look-back over the status words (one launch per pass) or the per-tile counts of ts2_hist + ts_scan.
 constexpr int OS2_ITEMS = 16;
 constexpr int OS2_TILE = OS_THREADS * OS2_ITEMS;   // 4096 pairs per tile
@@ -389,8 +389,13 @@ os2_pass(const uint32_t *__restrict__ kin, const uint32_t *__restrict__ vin, uin
         const int ia = wbase + k * 32 + lane, ib = ia + (OS2_ITEMS / 2) * 32;
         const bool va = ia < n, vb = ib < n;
         const uint32_t da = (key[k] >> shift) & mask, db = (key[k + OS2_ITEMS / 2] >> shift) & mask;
+#ifndef SPH_OS2_MATCH
+        // eight ballots per key; match.any measured 22 % slower per pass on sm_100a (profiles/r2/ab_sort.txt)
+        const uint32_t pa = os_match(da, va), pb = os_match(db, vb);
+#else
         const uint32_t pa = __match_any_sync(0xffffffffu, va ? da : (0x10000u + lane));
         const uint32_t pb = __match_any_sync(0xffffffffu, vb ? db : (0x10000u + lane));
+#endif
         uint32_t prea = 0, preb = 0;
         if (va) prea = sm.wcnt[2 * warp][da];
         if (vb) preb = sm.wcnt[2 * warp + 1][db];
@@ -415,6 +420,7 @@ os2_pass(const uint32_t *__restrict__ kin, const uint32_t *__restrict__ vin, uin
             status[tid] = OS_FLAG_PREFIX | tile_cnt;
         } else {
             status[(size_t)tile * OS_RADIX + tid] = OS_FLAG_AGG | tile_cnt;
+            // (looking back four predecessors per trip was measured: +7 % per pass -- the chains are short)
             int prev = tile - 1;
             while (true) {
                 const uint32_t s = status[(size_t)prev * OS_RADIX + tid];

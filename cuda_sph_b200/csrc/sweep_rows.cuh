@@ -39,7 +39,9 @@ namespace sph {
 constexpr int RB_THREADS = SPH_RB_THREADS;   // threads == particles per CTA (a tile)
 constexpr int RB_WARPS = RB_THREADS / 32;
 #ifndef SPH_RB_CAP
-#define SPH_RB_CAP (RB_THREADS == 128 ? 2048 : RB_THREADS == 64 ? 1536 : 3328)
+// 2240: the largest staging that keeps 3 force CTAs and 4 row-density CTAs per SM (static_asserts below); at 2048, 3.4 % of
+// the dam-break tiles (25 per cell) did not fit and ran as 32-particle passes: step 0.600 -> 0.563 ms at 2^20 particles
+#define SPH_RB_CAP (RB_THREADS == 128 ? 2240 : RB_THREADS == 64 ? 1536 : 3328)
 #endif
 constexpr int RB_CAP = SPH_RB_CAP;   // row slots per CTA pass (candidates staged in shared memory)
 constexpr int RB_MAXC = RB_THREADS / 2;                   // non-empty cells per CTA pass
@@ -118,6 +120,9 @@ struct ForceRowsSmem {
 
 // Neighbour cell `s` (0..26, dx outermost, dz innermost: voxel_kernels.py:46-48) of cell (cx, cy, cz): range of the
 // sorted arrays, (0, 0) if the cell is outside the domain / the local table.
+// 227 KB of shared memory per SM, 1 KB of it reserved per resident CTA
+static_assert((sizeof(ForceRowsSmem) + 1024) * RB_FORCE_CTAS <= 227 * 1024, "RB_FORCE_CTAS force CTAs per SM");
+static_assert((sizeof(DensityRowsSmem) + 1024) * RB_DENSITY_CTAS <= 227 * 1024, "RB_DENSITY_CTAS density CTAs per SM");
 __device__ __forceinline__ int2 neighbour_range(const SweepArgs &a, const GridDesc &g, int s, int cx, int cy, int cz) {
     const int x = cx + s / 9 - 1, y = cy + (s / 3) % 3 - 1, z = cz + s % 3 - 1;
     if (x >= 0 && x < g.tx && y >= 0 && y < g.ty && z >= 0 && z < g.tz) {
