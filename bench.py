@@ -356,11 +356,12 @@ def measure_single(name, args, local_rank, stream, flush, *, K, W, e2e_steps, wi
                 "stages_ms": stage_ms, "stages_gbs": stage_gbs,
                 "step_bytes_per_particle": sum(stage_bytes.values()),
                 "step_frac": sum(stage_bytes.values()) * value / 1e9 / hbm_peak,
-                "note": "the neighbour sweeps are bound by instruction issue and shared-memory return bandwidth at > 2 "
-                        "particles/cell (SURVEY 8d; ncu: 2-15 % DRAM throughput); the HBM fraction is reported as the "
-                        "contract asks; kernel_ms of the density stage includes its row-plan kernel; traffic exceeds the "
-                        "algorithmic bytes because the neighbour lists (64 B/particle) and pair factors are "
-                        "engine-internal"}
+                "note": "the neighbour sweeps are bound by shared-memory bandwidth and instruction issue, not HBM (ncu: "
+                        "LSU data pipe 60-80 % busy, 4-20 % DRAM throughput; DESIGN.md section 4); the HBM fraction is "
+                        "reported as the contract asks; kernel_ms of the density stage includes its row-plan kernel; "
+                        "traffic (ncu, dram read + write of the named kernel alone) exceeds the algorithmic bytes because "
+                        "the neighbour lists (64 B/particle) and the pair factors (two 4-byte lanes of 16-byte records = "
+                        "32 B of sectors per particle) are engine-internal"}
 
     # ---- e2e: compute_next_state through the C ABI with pinned fp64 host buffers ----------------------------------
     e2e = None

@@ -55,10 +55,11 @@ __device__ __forceinline__ int slab_owner(const SlabRoute &r, int col) {
 
 // One record into the block of destination `d` (all lanes of the warp call this; `emit` says which lanes have one).
 // kind 0 = migrant (first region of the block), 1 = ghost (second region).  Warp-aggregated: one atomic per (warp, destination, kind).
-__device__ __forceinline__ void slab_emit(const SlabRoute &r, unsigned char *sendbuf, int32_t *counters, bool emit,
+__device__ __forceinline__ bool slab_emit(const SlabRoute &r, unsigned char *sendbuf, int32_t *counters, bool emit,
                                           int d, int kind, const float4 &p, const float4 &v, int gid,
                                           const uint64_t *rng) {
     const unsigned lane = threadIdx.x & 31;
+    bool stored = false;   // false for a lane whose record did not fit its block (overflow: the caller keeps the particle)
     unsigned pending = __ballot_sync(0xffffffffu, emit);
     while (pending) {
         const int leader = __ffs(pending) - 1;
@@ -88,9 +89,11 @@ __device__ __forceinline__ void slab_emit(const SlabRoute &r, unsigned char *sen
                     }
                     *reinterpret_cast<ulonglong2 *>(rec + 32) = make_ulonglong2(s0, s1);
                 }
+                stored = true;
             }
         }
     }
+    return stored;
 }
 
 __global__ void __launch_bounds__(256)
@@ -113,10 +116,10 @@ slab_route_kernel(SlabRoute r, float4 *__restrict__ pos_m, const float4 *__restr
     const int lo = r.bounds[o], hi = r.bounds[o + 1];
     const bool ghost_l = have && o > 0 && col >= lo && col < lo + SLAB_HALO;
     const bool ghost_r = have && o < r.world - 1 && col >= hi - SLAB_HALO && col < hi;
-    slab_emit(r, sendbuf, counters, leaves, o, 0, p, v, g, rng);
+    const bool sent = slab_emit(r, sendbuf, counters, leaves, o, 0, p, v, g, rng);
     slab_emit(r, sendbuf, counters, ghost_l, o - 1, 1, p, v, g, nullptr);
     slab_emit(r, sendbuf, counters, ghost_r, o + 1, 1, p, v, g, nullptr);
-    if (leaves) {   // the slot becomes a hole
+    if (leaves && sent) {   // the slot becomes a hole -- only if the record left: on overflow the particle stays (flagged)
         gid[i] = -1;
         pos_m[MI(i)] = make_float4(__int_as_float(0x7fc00000), 0.f, 0.f, 0.f);
     }
@@ -201,6 +204,7 @@ slab_route_cta_kernel(const __grid_constant__ SlabEmit em, float4 *__restrict__ 
     __syncthreads();
     if (rec[0] || rec[1] || rec[2]) {
         const float4 v = vel_m[MI(i)];
+        bool kept = false;   // migrant record did not fit: the particle stays with this rank (and the overflow flag is up)
 #pragma unroll
         for (int u = 0; u < 3; ++u) {
             if (!rec[u]) continue;
@@ -209,6 +213,7 @@ slab_route_cta_kernel(const __grid_constant__ SlabEmit em, float4 *__restrict__ 
             const int cap = kind == 0 ? r.cap_m[d] : r.cap_g[d];
             if (mine >= cap) {
                 atomicOr(&em.counters[SLAB_OVERFLOW], 1);
+                if (u == 0) kept = true;
                 continue;
             }
             const int slot = kind == 0 ? mine : r.cap_m[d] + mine;
@@ -224,7 +229,7 @@ slab_route_cta_kernel(const __grid_constant__ SlabEmit em, float4 *__restrict__ 
                 *reinterpret_cast<ulonglong2 *>(out + 32) = make_ulonglong2(s0, s1);
             }
         }
-        if (rec[0]) {   // the slot becomes a hole
+        if (rec[0] && !kept) {   // the slot becomes a hole
             gid[i] = -1;
             pos_m[MI(i)] = make_float4(__int_as_float(0x7fc00000), 0.f, 0.f, 0.f);
         }

@@ -254,8 +254,41 @@ rows_plan_kernel(const SweepArgs a, const GridDesc g, TilePlan *__restrict__ pla
     const int tile = blockIdx.x * RP_WARPS + (threadIdx.x >> 5);
     if (tile >= ntiles) return;
     const int p0 = tile * RB_THREADS;
-    int lo = INT_MAX, hi = 0;   // lanes 0..8: row `lane`
+    // The tile's cells come in RUNS of ascending x inside one grid row (cy, cz) -- one run, two where the tile wraps into
+    // the next grid row.  Row (dy, dz) of a run with cells xa .. xb is the hull of the non-empty cells
+    // (xa - 1 .. xb + 1, cy + dy, cz + dz): 32 cell ranges per trip, one lane each, first / last non-empty by ballot.
+    // (The first version fetched the 27 neighbour ranges of every cell: 432 loads and index computations for 16 cells where
+    // this one needs ~170, and 2030 warp instructions per tile.)
+    int lo[9], hi[9];   // warp-uniform
+#pragma unroll
+    for (int r = 0; r < 9; ++r) {
+        lo[r] = INT_MAX;
+        hi[r] = 0;
+    }
+    auto flush = [&](int xa, int xb, int cy, int cz) {
+#pragma unroll
+        for (int r = 0; r < 9; ++r) {
+            const int y = cy + r / 3 - 1, z = cz + r % 3 - 1;
+            if (y < 0 || y >= g.ty || z < 0 || z >= g.tz) continue;
+            const long long rowbase = (long long)y * g.wn + (long long)z * g.wn * g.hn - g.xoff;
+            for (int x0 = xa - 1; x0 <= xb + 1; x0 += 32) {
+                const int x = x0 + lane;
+                int2 rg = make_int2(0, 0);
+                if (x <= xb + 1 && x >= 0 && x < g.tx) {
+                    const long long cl = rowbase + x;
+                    if (cl >= 0 && cl < g.ncells) rg = __ldg(&a.cell_range[cl]);
+                }
+                const unsigned ne = __ballot_sync(FULL, rg.y > rg.x);
+                if (ne) {
+                    lo[r] = min(lo[r], __shfl_sync(FULL, rg.x, __ffs(ne) - 1));
+                    hi[r] = max(hi[r], __shfl_sync(FULL, rg.y, 31 - __clz(ne)));
+                }
+            }
+        }
+    };
     int ncell = 0;
+    bool run = false;
+    int run_xa = 0, run_xb = 0, run_y = 0, run_z = 0;   // warp-uniform
     for (int chunk = 0; chunk < RB_THREADS / 32; ++chunk) {
         const int t = p0 + chunk * 32 + lane;
         const uint32_t key = (t < a.n) ? a.skeys[t] : (uint32_t)g.ncells;
@@ -263,40 +296,38 @@ rows_plan_kernel(const SweepArgs a, const GridDesc g, TilePlan *__restrict__ pla
         const bool first = live && ((chunk == 0 && lane == 0) || a.skeys[t - 1] != key);
         unsigned todo = __ballot_sync(FULL, first);
         ncell += __popc(todo);
-        while (todo) {   // four cells per trip: their range loads are independent, issue them together
-            int2 r[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                r[u] = make_int2(0, 0);
-                if (todo) {
-                    const int src = __ffs(todo) - 1;
-                    todo &= todo - 1;
-                    const uint32_t ckey = __shfl_sync(FULL, key, src);
-                    int cx, cy, cz;
-                    decode_cell(g, ckey, cx, cy, cz);
-                    if (lane < 27) r[u] = neighbour_range(a, g, lane, cx, cy, cz);
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                // rows are (dy, dz) = lane % 9; the three dx cells of a row sit in lanes r, r + 9, r + 18
-                const int l3 = (r[u].y > r[u].x) ? r[u].x : INT_MAX, h3 = (r[u].y > r[u].x) ? r[u].y : 0;
-                const int l9 = __shfl_down_sync(FULL, l3, 9), h9 = __shfl_down_sync(FULL, h3, 9);
-                const int l18 = __shfl_down_sync(FULL, l3, 18), h18 = __shfl_down_sync(FULL, h3, 18);
-                if (lane < 9) {
-                    lo = min(lo, min(l3, min(l9, l18)));
-                    hi = max(hi, max(h3, max(h9, h18)));
-                }
+        int cx = 0, cy = 0, cz = 0;
+        if (first) decode_cell(g, key, cx, cy, cz);
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int x = __shfl_sync(FULL, cx, src), y = __shfl_sync(FULL, cy, src), z = __shfl_sync(FULL, cz, src);
+            if (run && y == run_y && z == run_z && x > run_xb) {
+                run_xb = x;
+            } else {
+                if (run) flush(run_xa, run_xb, run_y, run_z);
+                run = true;
+                run_xa = run_xb = x;
+                run_y = y;
+                run_z = z;
             }
         }
     }
-    const int len = (lane < 9) ? max(hi - lo, 0) : 0;
+    if (run) flush(run_xa, run_xb, run_y, run_z);
+    int lo_l = INT_MAX, hi_l = 0;   // lanes 0..8: row `lane`
+#pragma unroll
+    for (int r = 0; r < 9; ++r)
+        if (lane == r) {
+            lo_l = lo[r];
+            hi_l = hi[r];
+        }
+    const int len = (lane < 9) ? max(hi_l - lo_l, 0) : 0;
     int sum = len;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(FULL, sum, o);
     TilePlan &tp = plans[tile];
     if (lane < 9) {
-        tp.row_lo[lane] = (len > 0) ? lo : 0;
+        tp.row_lo[lane] = (len > 0) ? lo_l : 0;
         tp.row_len[lane] = len;
     }
     if (lane == 0) {
