@@ -136,6 +136,12 @@ def run(args, rank, world, local_rank):
             acc[k_] = acc.get(k_, 0.0) + v_ / (window or 4)
     keys_ = sorted(acc)
     bt = torch.tensor([acc[k_] for k_ in keys_], device=dev, dtype=torch.float64)
+    # per rank: the work of its own step (everything except the wait at the flag barrier / inside the all_to_all), to see
+    # how well the slab boundaries balance it
+    own_work = torch.tensor([sum(v_ for k_, v_ in acc.items() if k_ not in ("flag_barrier_ms", "all_to_all_ms"))],
+                            device=dev, dtype=torch.float64)
+    work_all = [torch.empty_like(own_work) for _ in range(world)]
+    dist.all_gather(work_all, own_work)
     dist.all_reduce(bt, op=dist.ReduceOp.MAX)
     breakdown = {k_: float(v_) for k_, v_ in zip(keys_, bt.tolist())}
     stt = run_.check()
@@ -211,7 +217,8 @@ def run(args, rank, world, local_rank):
                 "owned_high_water_per_rank": [int(s[1]) for s in allstats],
                 "owned_per_rank": [int(s[2]) for s in allstats],
                 "exchange_bytes_per_step_per_rank": int(sum(run_.block_bytes)),
-                "phase_ms_max_over_ranks": breakdown}
+                "phase_ms_max_over_ranks": breakdown,
+                "work_ms_per_rank": [round(float(w_.item()), 4) for w_ in work_all]}
         print(json.dumps(line), flush=True)
     run_.close()
     dist.barrier()

@@ -88,15 +88,41 @@ fix_order_kernel(const uint32_t *__restrict__ skeys, const uint32_t *__restrict_
                  uint32_t *__restrict__ sids_out, const int32_t *__restrict__ gid,
                  const int2 *__restrict__ cell_range, int n, uint32_t dead_key) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n) return;
-    const uint32_t me = sids_in[t];
-    if (skeys[t] == dead_key) {   // dead cell (incl. every empty slot): nobody's candidate, keep the order
+    const int lane = threadIdx.x & 31;
+    const bool in = t < n;
+    const uint32_t key = in ? skeys[t] : dead_key;
+    const uint32_t me = in ? sids_in[t] : 0u;
+    const bool live = in && key != dead_key;
+    const int32_t g = live ? gid[me] : 0;
+    // A cell that lies inside this warp's 32 sorted positions is ranked by shuffles (one gather of the global id per
+    // particle instead of one per pair); a cell that continues into a neighbouring warp takes the table walk below.
+    const uint32_t up = __shfl_up_sync(0xffffffffu, key, 1);
+    const unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || up != key);
+    const int start = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));            // first lane of my cell
+    const unsigned after = heads & ~(0xffffffffu >> (31 - lane));                     // heads behind me
+    const int end = after ? __ffs(after) - 1 : 32;                                     // one past its last lane
+    bool inside = live;
+    if (live && start == 0 && t - lane > 0 && skeys[t - lane - 1] == key) inside = false;          // began in the previous warp
+    if (live && end == 32 && t - lane + 32 < n && skeys[t - lane + 32] == key) inside = false;     // continues in the next
+    int len = inside ? end - start : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) len = max(len, __shfl_xor_sync(0xffffffffu, len, o));
+    int rank = 0;
+    for (int k = 0; k < len; ++k) {
+        const int src = start + k;
+        const int32_t v = __shfl_sync(0xffffffffu, g, src & 31);
+        if (inside && src < end) rank += (v < g) ? 1 : 0;
+    }
+    if (!in) return;
+    if (!live) {   // dead cell (incl. every empty slot): nobody's candidate, keep the order
         sids_out[t] = me;
         return;
     }
-    const int2 r = cell_range[skeys[t]];
-    const int32_t g = gid[me];
-    int rank = 0;
+    if (inside) {
+        sids_out[t - (lane - start) + rank] = me;
+        return;
+    }
+    const int2 r = cell_range[key];
     for (int u = r.x; u < r.y; ++u) rank += (gid[sids_in[u]] < g) ? 1 : 0;
     sids_out[r.x + rank] = me;
 }
