@@ -399,8 +399,12 @@ int sph_create(const SphParams *params, int device, sph_handle_t *out) {
                          (int)sizeof(ForceRowsSmem));
     cudaFuncSetAttribute(force_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)sizeof(ForceRowsSmem));
-    e->launches_per_step = ((e->onesweep && e->sort_gen2) ? 0 : 1) + (e->onesweep ? 2 + (e->sort_lookback ? 1 : 3) * e->passes : 3 * e->passes) + 1 + 1 + 1 + 1 +
-                           (e->rows_sweeps ? (e->flat_density ? 4 : 3) : 0);
+    // launches of one step (kernels + the two memsets), as enqueue_step issues them on a single GPU
+    e->launches_per_step =
+        ((e->onesweep && e->sort_gen2) ? 0 : 1)                                                      // hash (fused into hash_hist otherwise)
+        + (e->onesweep ? 2 + (e->sort_lookback ? 1 : 3) * e->passes : 3 * e->passes)                  // memset + histogram + passes
+        + 2                                                                                          // memset(cell_range), reorder
+        + (e->rows_sweeps ? 1 /* rows_plan */ + (e->flat_density ? 4 + 3 : 2 + 2) : 2);              // density + force kernels
     if (cudaDeviceSynchronize() != cudaSuccess) {
         sph_destroy(e);
         return fail("device error during create");

@@ -51,12 +51,17 @@ def equal_count_bounds(col_hist: np.ndarray, world: int, min_width: int = HALO) 
     return bounds
 
 
-def balanced_bounds(col_hist: np.ndarray, world: int, ghost_weight: float = 0.6, min_width: int = HALO) -> List[int]:
+def balanced_bounds(col_hist: np.ndarray, world: int, ghost_weight: float = 1.25, min_width: int = HALO) -> List[int]:
     """Column boundaries that balance the WORK of a step rather than the owned count: a rank hashes, sorts and stages its
     ghosts too (two columns per interior side), so the cost of slab [lo, hi) is
         sum(hist[lo:hi]) + ghost_weight * (hist[lo - HALO:lo] if lo > 0) + ghost_weight * (hist[hi:hi + HALO] if hi < W).
     Minimises the maximum cost over ranks (binary search on the bound, greedy sweep).  With whole-column slabs this puts
-    the wider slabs at the domain ends, where there is only one halo."""
+    the wider slabs at the domain ends, where there is only one halo.
+
+    ghost_weight: measured, not guessed -- per-rank work of a box32m step (bench line `work_ms_per_rank`): 4 GPUs, slabs
+    41|40|40|41 columns: 4.46 ms at the ends, 4.63 ms inside; 8 GPUs, 21|20x6|21: 2.47 / 2.64 ms.  Both give a ghost column
+    the cost of 1.2-1.3 owned columns (it is hashed, sorted, staged, gets a density if it is the inner one, and is routed
+    and unpacked on top)."""
     hist = np.asarray(col_hist, np.float64)
     w = len(hist)
     if w < world * min_width:

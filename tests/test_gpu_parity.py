@@ -228,6 +228,21 @@ def test_dense_cells_take_the_fallback_passes(n, ppc, seed):
     # grid / sort / neighbour counts stay bit-exact; at 140 particles per cell (rho ~ 18 rho_0, |F| ~ 1e4) the fp32
     # pair sums cancel harder and the box is only 14 units wide, so the RELATIVE position tolerance is widened there
     _check_against(s, _oracle_ref(P, st.position, st.velocity), vec=1e-4 if ppc < 100 else 5e-4)
+    # ... and these cases really leave the main sweeps (sph_path_counters: work items of the step just run)
+    pc = s.path_counters()
+    assert pc["tiles"] == (n + 127) // 128 and pc["passes"] + pc["dense_tiles"] > 0, pc
+    s.close()
+
+
+def test_path_counters_main_path():
+    """At the reference's own densities every tile runs on the main sweeps: no fallback work items."""
+    from cuda_sph_b200 import workloads
+    n = 100000
+    params, st = workloads.uniform_box(n, 8.0, seed=5)
+    s = _strategy(n, "BOX", params.space_size, params.voxel_size, params.external_force, params.fps)
+    s.compute_next_state(st)
+    pc = s.path_counters()
+    assert pc == dict(passes=0, flat_refused=0, dense_tiles=0, tiles=(n + 127) // 128), pc
     s.close()
 
 
