@@ -198,10 +198,6 @@ int sph_create(const SphParams *params, int device, sph_handle_t *out) {
         return fail("no CUDA device: libsph_b200 has no CPU fallback");
     if (device < 0 || device >= ndev) return fail("bad device index");
     CK(cudaSetDevice(device));
-    if (const char *lf = getenv("SPH_L2_FETCH")) {   // A/B knob: L2 fetch granularity hint (32 / 64 / 128 bytes)
-        cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(lf));
-        cudaGetLastError();
-    }
 
     SphEngine *e = new SphEngine();
     e->p = *params;
