@@ -470,6 +470,10 @@ class NativeSlabRunner:
         self._lib = _lib.load()
         self._chk = _lib.check
         cst = constants or SphConstants()
+        # what rebalanced() needs to build the successor of this runner
+        self._ctor = dict(params=params, constants=constants, device=device, group=group, own_slack=own_slack,
+                          ghost_slack=ghost_slack, migrant_frac=migrant_frac, far_frac=far_frac,
+                          compact_every=compact_every, poll_every=poll_every, p2p=p2p)
         self.group = group
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -631,6 +635,77 @@ class NativeSlabRunner:
         self.counters[0] = k
         self.steps = 0
         self.exchange()
+
+    # ------------------------------------------------------------------ load balance
+    def column_histogram(self) -> np.ndarray:
+        """Particles per cell column over ALL ranks, from the current owned positions."""
+        own = torch.nonzero(self.G[:self.own_cap] >= 0).flatten()
+        x = self.P[own, 0].to(torch.float64) / self.voxel_x
+        col = torch.where(torch.isfinite(x), x, torch.zeros_like(x)).to(torch.int64).clamp_(0, self.n_cols - 1)
+        hist = torch.bincount(col, minlength=self.n_cols).to(torch.int64)
+        if self.world > 1:
+            dist.all_reduce(hist, group=self.group)
+        return hist.cpu().numpy()
+
+    def rebalanced(self, min_gain: float = 0.03) -> "NativeSlabRunner":
+        """Slab boundaries re-evaluated from the CURRENT particle distribution (a dam break spreads out; the boundaries of
+        the start state then leave most of the work to one rank).  Returns this runner if the work-balanced boundaries
+        (balanced_bounds) would lower the maximum per-rank cost by less than `min_gain`; otherwise a NEW runner that owns
+        the same particles (same global ids, positions, velocities, xoroshiro states) under the new boundaries -- this one
+        is closed.  Stop-the-world and host-mediated (gather by global id, reload): meant for every k >> 1 steps, off the
+        step path; the particles' state is carried in fp32 exactly, so the run continues bit for bit."""
+        hist = self.column_histogram()
+        new_bounds = [int(b) for b in balanced_bounds(hist, self.world)]
+        if new_bounds == self.bounds:
+            return self
+
+        def max_cost(bounds):
+            cum = np.concatenate([[0], np.cumsum(hist)])
+            cost = []
+            for r in range(self.world):
+                lo, hi = bounds[r], bounds[r + 1]
+                c = cum[hi] - cum[lo]
+                c += 1.25 * (cum[lo] - cum[max(lo - HALO, 0)]) + 1.25 * (cum[min(hi + HALO, self.n_cols)] - cum[hi])
+                cost.append(c)
+            return max(cost)
+        if max_cost(new_bounds) > (1.0 - min_gain) * max_cost(self.bounds):
+            return self
+        pos, vel, _ = self.gather_global(self.n_global)
+        rng = None
+        if self.R is not None:   # the xoroshiro state of a particle lives with its owner: collect by global id
+            own = torch.nonzero(self.G[:self.own_cap] >= 0).flatten()
+            gids = self.G[own].to(torch.int64)
+            rng = torch.zeros_like(self.R)
+            rng[gids] = self.R[gids]
+            if self.world > 1:
+                dist.all_reduce(rng, group=self.group)
+        kw = dict(self._ctor)
+        params, constants = kw.pop("params"), kw.pop("constants")
+        steps = self.steps
+        torch.cuda.synchronize()
+        if self.world > 1:
+            dist.barrier(group=self.group)   # nobody is still pushing into a buffer that is about to be unmapped
+        self.close()
+        if self.world > 1:
+            dist.barrier(group=self.group)
+        new = NativeSlabRunner(params, constants, col_hist=hist, bounds=new_bounds, **kw)
+        new.load_global(pos, vel)
+        if rng is not None:
+            new.R.copy_(rng)
+        new.steps = steps
+        return new
+
+    def run(self, n_steps: int, rebalance_every: int = 0, min_gain: float = 0.03) -> "NativeSlabRunner":
+        """n_steps steps with the slab boundaries re-evaluated every `rebalance_every` steps (0: never).  Returns the
+        runner that holds the state afterwards (rebalanced() replaces the runner when the boundaries move)."""
+        runner, done = self, 0
+        while done < n_steps:
+            g = min(rebalance_every or n_steps, n_steps - done)
+            runner.step(g)
+            done += g
+            if rebalance_every and done < n_steps:
+                runner = runner.rebalanced(min_gain)
+        return runner
 
     def step(self, n_steps: int = 1) -> None:
         """Between steps the state is AT REST: every particle sits with its owner and the ghost region holds the halos of

@@ -64,6 +64,60 @@ def _worker(rank, world, port, mode, n, steps, extra_steps, out_path, kind="nati
         dist.destroy_process_group()
 
 
+def _rebalance_worker(rank, world, port, n, out_path):
+    import faulthandler
+    import torch.distributed as dist
+    faulthandler.dump_traceback_later(150, exit=True)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from cuda_sph_b200 import SphConstants, workloads
+        from cuda_sph_b200.slab import NativeSlabRunner, equal_count_bounds
+        params, st = workloads.dam_break(n, 0.5, seed=7)
+        n_cols = int(np.ceil(params.space_size[0] / params.voxel_size[0]))
+        cols = np.clip((st.position[:, 0] / params.voxel_size[0]).astype(np.int64), 0, n_cols - 1)
+        hist = np.bincount(cols, minlength=n_cols)
+        bounds = equal_count_bounds(hist, world)
+        run = NativeSlabRunner(params, SphConstants(mode="BOX"), col_hist=hist, bounds=bounds, device=rank,
+                               compact_every=2, migrant_frac=0.5, own_slack=2.0)
+        run.load_global(st.position, st.velocity)
+        run.step(2)
+        old_bounds = list(run.bounds)
+        run2 = run.rebalanced(min_gain=0.0)          # the column has spread: new boundaries, new runner, same particles
+        changed = run2 is not run
+        run2.step(2)
+        assert run2.count_global() == n
+        pos, vel, rho = run2.gather_global(n)
+        if rank == 0:
+            np.savez(out_path, pos=pos, vel=vel, rho=rho, changed=changed, old=old_bounds, new=list(run2.bounds))
+        run2.close()
+    finally:
+        faulthandler.cancel_dump_traceback_later()
+        dist.destroy_process_group()
+
+
+def test_two_gpu_rebalance_continues_bitwise(tmp_path):
+    """SURVEY section 7 "Load balance": slab boundaries re-evaluated between steps of a dam break.  The run with new
+    boundaries (new runner, particles re-owned by global id) must continue bit for bit like the single-GPU engine."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    from cuda_sph_b200 import B200SPHStrategy, SphConstants, workloads
+    n, out = 150000, str(tmp_path / "rebalance.npz")
+    mp.spawn(_rebalance_worker, args=(2, _free_port(), n, out), nprocs=2, join=True)
+    got = np.load(out)
+    assert bool(got["changed"]) and list(got["old"]) != list(got["new"])
+    params, st = workloads.dam_break(n, 0.5, seed=7)
+    s = B200SPHStrategy(params, SphConstants(mode="BOX"))
+    s.upload(st)
+    s.step(4)
+    ref = s.download()
+    s.close()
+    eq = lambda a, b: bool(np.all((a == b) | (np.isnan(a) & np.isnan(b))))  # noqa: E731
+    assert eq(got["pos"], ref.position) and eq(got["vel"], ref.velocity) and eq(got["rho"], ref.density)
+
+
 def _case(mode, n):
     from cuda_sph_b200 import config, workloads
     if mode == "BOX":
