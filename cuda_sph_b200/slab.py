@@ -183,16 +183,16 @@ class SlabRunner:
         if at + k > self.P.shape[0]:
             raise RuntimeError(f"slab capacity exceeded on rank {self.rank}: {at + k} > {self.P.shape[0]}")
         pb = self.P.element_size() * 4
-        o = 0
-        self.P[at:at + k] = rows[:, o:o + pb].contiguous().view(self.P.dtype).reshape(k, 4)
+        o = 0   # (.reshape(-1).clone(): a one-row slice keeps the wide row stride through .contiguous(), which view() rejects)
+        self.P[at:at + k] = rows[:, o:o + pb].reshape(-1).clone().view(self.P.dtype).reshape(k, 4)
         o += pb
-        self.V[at:at + k] = rows[:, o:o + pb].contiguous().view(self.V.dtype).reshape(k, 4)
+        self.V[at:at + k] = rows[:, o:o + pb].reshape(-1).clone().view(self.V.dtype).reshape(k, 4)
         o += pb
-        gid = rows[:, o:o + 4].contiguous().view(torch.int32).reshape(k)
+        gid = rows[:, o:o + 4].reshape(-1).clone().view(torch.int32).reshape(k)
         self.G[at:at + k] = gid
         o += 4
         if with_rng and self.R is not None:
-            self.R[gid.long()] = rows[:, o:o + 16].contiguous().view(torch.int64).reshape(k, 2)
+            self.R[gid.long()] = rows[:, o:o + 16].reshape(-1).clone().view(torch.int64).reshape(k, 2)
         return k
 
     # ------------------------------------------------------------------ one step
@@ -232,6 +232,34 @@ class SlabRunner:
             self._local_step(self.n_own, self.n_local)
             self.migrate()
             self.stats["steps"] += 1
+
+    # ------------------------------------------------------------------ load balance
+    def column_histogram(self) -> np.ndarray:
+        """Owned particles per cell column, summed over the ranks."""
+        col = self.columns(self.P[:self.n_own, 0]).clamp(0, self.n_cols - 1)
+        hist = torch.bincount(col.cpu(), minlength=self.n_cols).to(torch.int64)
+        if self.world > 1:
+            dist.all_reduce(hist, group=self.group)
+        return hist.numpy()
+
+    def _set_bounds(self, bounds: Sequence[int]) -> None:
+        self.bounds = [int(b) for b in bounds]
+        self.lo, self.hi = self.bounds[self.rank], self.bounds[self.rank + 1]
+
+    def rebalance(self) -> bool:
+        """Between steps: re-evaluate the slab boundaries from the current distribution (balanced_bounds) and hand every
+        particle to its new owner.  This protocol-level version moves the boundaries in place -- the particles whose
+        column changed hands are ordinary migrants; NativeSlabRunner.rebalanced() rebuilds the fixed-capacity device
+        layout instead.  Returns True if the boundaries moved."""
+        new_bounds = [int(b) for b in balanced_bounds(self.column_histogram(), self.world)]
+        if new_bounds == self.bounds:
+            return False
+        self._set_bounds(new_bounds)
+        self._after_rebound()
+        return True
+
+    def _after_rebound(self) -> None:
+        self.migrate()          # at rest every particle sits with its owner again
 
     # ------------------------------------------------------------------ loading / gathering
     def load_global(self, position: np.ndarray, velocity: np.ndarray) -> None:
@@ -321,6 +349,9 @@ class SingleExchangeSlabRunner(SlabRunner):
             self.route_and_exchange()
             self._local_step(self.n_own, self.n_local)
             self.stats["steps"] += 1
+
+    def _after_rebound(self) -> None:
+        pass                    # the next step's routing sends everybody to the owner under the new boundaries
 
 
 class _CudaBuffer:

@@ -131,6 +131,55 @@ def test_slab_decomposition_matches_single_domain_bitwise(tmp_path, world, mode,
     assert all(b - a >= HALO for a, b in zip(got["bounds"][:-1], got["bounds"][1:]))
 
 
+def _rebalance_worker(rank, world, port, out_path, single_exchange):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        orc.set_exact_pow(False)
+        orc.set_num_threads(1)
+        n, params, st, P = _dam_case()
+        n_cols = int(np.ceil(params.space_size[0] / params.voxel_size[0]))
+        cols = np.clip((st.position[:, 0] / params.voxel_size[0]).astype(np.int64), 0, n_cols - 1)
+        bounds = equal_count_bounds(np.bincount(cols, minlength=n_cols), world)
+        cls = OracleSingleExchangeRunner if single_exchange else OracleSlabRunner
+        run = cls(P, n, capacity=2 * n, n_cols=n_cols, bounds=bounds, pipe_mode=False)
+        run.load_global(st.position, st.velocity)
+        run.step(2)
+        moved = run.rebalance()                              # the column has spread: the boundaries move
+        new_bounds = list(run.bounds)
+        run.step(2)
+        assert run.count_global() == n
+        pos, vel, rho = run.gather_global(n)
+        if rank == 0:
+            np.savez(out_path, pos=pos, vel=vel, rho=rho, moved=moved, old=np.asarray(bounds), new=np.asarray(new_bounds))
+    finally:
+        dist.destroy_process_group()
+
+
+def _dam_case():
+    n = 6000
+    params, st = workloads.dam_break(n, 0.5, seed=7)
+    P = orc.OracleParams(n=n, mode="BOX", space=tuple(params.space_size), dt=1 / params.fps)
+    return n, params, st, P
+
+
+@pytest.mark.parametrize("single_exchange", [False, True], ids=["two-exchanges", "single-exchange"])
+def test_rebalance_between_steps_continues_bitwise(tmp_path, single_exchange):
+    """SURVEY section 7 "Load balance": boundaries re-evaluated between steps of a dam break (world 2, gloo).  Two steps,
+    rebalance, two more steps == four steps of the single-domain oracle, bit for bit."""
+    out = str(tmp_path / "rebalance.npz")
+    mp.spawn(_rebalance_worker, args=(2, _free_port(), out, single_exchange), nprocs=2, join=True)
+    got = np.load(out)
+    assert bool(got["moved"]) and list(got["old"]) != list(got["new"])
+    orc.set_exact_pow(False)
+    n, params, st, P = _dam_case()
+    pos, vel, rho = st.position, st.velocity, None
+    for _ in range(4):
+        r = orc.step(P, pos, vel, light=True)
+        pos, vel, rho = r.position, r.velocity, r.density
+    assert same(got["pos"], pos) and same(got["vel"], vel) and same(got["rho"], rho)
+
+
 def test_equal_count_bounds():
     hist = np.zeros(75, np.int64)
     hist[:8] = 1000                                          # dam-break column: everything in the first columns
