@@ -286,6 +286,29 @@ def test_kernel_variants_agree(monkeypatch):
     assert vec_rel(a.position, b.position) < 1e-5
 
 
+def test_sort_variants_agree(monkeypatch):
+    """Every sort organisation (second generation: look-back (default) and count + scan; first generation: look-back,
+    count + scan; the three-kernel passes) yields the same (key, id) order -- numpy's lexsort((id, key)) -- on an input
+    of many tiles with a ragged last one."""
+    from cuda_sph_b200 import workloads
+    n = 300007
+    params, st = workloads.uniform_box(n, 8.0, seed=35)
+    ref = None
+    for sort in (None, "count2", "lookback", "count", "classic"):
+        if sort is None:
+            monkeypatch.delenv("SPH_SORT", raising=False)
+        else:
+            monkeypatch.setenv("SPH_SORT", sort)
+        s = _strategy(n, "BOX", params.space_size, params.voxel_size, params.external_force, params.fps)
+        s.upload(st)
+        s.step(1)
+        keys, ids = s.keys(), s.sorted_ids()
+        s.close()
+        if ref is None:
+            ref = np.lexsort((np.arange(n), keys))
+        assert np.array_equal(ids, ref), sort
+
+
 @pytest.mark.parametrize("maker,n,arg,seed", [("dam", 60000, 2.5, 41), ("box", 50000, 2.5, 42), ("box", 50000, 8.0, 43),
                                               ("box", 60000, 25.0, 44), ("box", 40000, 45.0, 45),
                                               ("box", 40000, 111.0, 46), ("box", 60000, 260.0, 47)])
