@@ -355,8 +355,11 @@ ts2_hist(const uint32_t *__restrict__ keys, int n, int shift, uint32_t mask, uin
     tile_cnt[(size_t)tid * ntiles + blockIdx.x] = hist[tid];
 }
 
+#ifndef SPH_OS2_CTAS
+#define SPH_OS2_CTAS 3
+#endif
 template <bool LOOKBACK>
-__global__ void __launch_bounds__(OS_THREADS, 3)
+__global__ void __launch_bounds__(OS_THREADS, SPH_OS2_CTAS)
 os2_pass(const uint32_t *__restrict__ kin, const uint32_t *__restrict__ vin, uint32_t *__restrict__ kout,
          uint32_t *__restrict__ vout, int n, int pass, int n_passes, int shift, uint32_t mask, int ntiles,
          uint32_t *__restrict__ ctrl, const uint32_t *__restrict__ tile_off) {

@@ -50,7 +50,10 @@ constexpr int RB_DENSITY_CTAS = RB_THREADS == 128 ? 4 : RB_THREADS == 64 ? 6 : 2
 #define SPH_RB_FORCE_CTAS (RB_THREADS == 128 ? 3 : RB_THREADS == 64 ? 4 : 2)
 #endif
 constexpr int RB_FORCE_CTAS = SPH_RB_FORCE_CTAS;
-constexpr int PF_AHEAD = 148 * 4;   // L2 prefetch distance of the sweeps, in tiles (about one wave of resident CTAs)
+#ifndef SPH_PF_AHEAD
+#define SPH_PF_AHEAD (148 * 4)
+#endif
+constexpr int PF_AHEAD = SPH_PF_AHEAD;   // L2 prefetch distance of the sweeps, in tiles (about one wave of resident CTAs)
 constexpr int RB_KEEP = 33;       // superset candidates kept per particle (32 + spares for rejected band candidates)
 constexpr int RB_LSTRIDE = 38;    // uint16 per list row (19 words: conflict-free rows; >= RB_KEEP + 1)
 
