@@ -4,15 +4,19 @@
 // included) with sqrt(r^2) <= INF_R when its <= 27 cells are walked dx outermost / dz innermost, every cell in ascending
 // particle id; the density is the poly6 sum over that list (self skipped).
 //
-// What bounds this sweep is instruction issue and shared-memory return bandwidth, not HBM (a capped particle tests ~215
-// candidates to find its 32), so the organisation is about instructions and shared-memory bytes per candidate test:
+// What bounds this sweep is the shared-memory data pipe (78 % busy at 8 particles per cell: a broadcast LDS.128 still
+// delivers 16 bytes to each of 32 lanes) and instruction issue (47 %), not HBM (7 %): a capped particle tests ~215
+// candidates to find its 32.  So the organisation is about instructions and shared-memory bytes per candidate test:
 //   * column blocks.  The walk of a cell (cx, cy, cz) is B(cx-1) ++ B(cx) ++ B(cx+1) with B(x) = the 9 cells
 //     (x, cy+dy, cz+dz), dy outer / dz inner.  For the x-consecutive cells of a tile the blocks are staged ONCE, in
 //     column order, so the candidate sequence of EVERY cell is a contiguous window of the staged arrays (as many staged
 //     candidates as the row staging of sweep_rows.cuh, but one flat loop per particle instead of 27 segment loops).
-//   * staging: eight lanes per segment copy the candidates straight from the sorted positions into three SoA arrays
-//     (x | y | z, 12 B per candidate; up to four independent 16-B loads per lane in flight).  The copies are gathers of
-//     short runs into a transposed layout, which TMA bulk copies cannot produce (a first version staged AoS rows by
+//   * staging: one 16-byte descriptor per segment (first sorted index, length, staged position, first row slot), eight
+//     lanes per segment copy the candidates straight from the sorted positions into three SoA arrays (x | y | z, 12 B
+//     per candidate): short segments (<= 16 candidates: everything at <= 8 particles per cell) by 4-byte cp.async, so that
+//     all copies of the tile are in flight before the first wait; the tail of longer segments by 16-byte loads through
+//     registers (a 4-byte cp.async costs the L1 as many sectors as a 16-byte load).  The copies are gathers of short
+//     runs into a transposed layout, which TMA bulk copies cannot produce (a first version staged AoS rows by
 //     cp.async.bulk and transposed in place: the transposed groups cost 4-way bank conflicts in every later access).
 //   * scan: lane = particle, all lanes of a warp step through their windows in lockstep (broadcast LDS.128, four
 //     candidates per vector).  Per PAIR of candidates three FADD2 + three FFMA2 (packed f32x2) evaluate
