@@ -11,6 +11,7 @@ cases = [("dam-break 25/cell", "BOX", workloads.dam_break(8192, 2.5, seed=0)),
          ("uniform 60/cell (32-particle passes)", "BOX", workloads.uniform_box(12000, 60.0, seed=1)),
          ("uniform 140/cell (walk)", "BOX", workloads.uniform_box(8000, 140.0, seed=2)),
          ("uniform 2.5/cell", "BOX", workloads.uniform_box(6000, 2.5, seed=3)),
+         ("uniform 8/cell, several sort tiles", "BOX", workloads.uniform_box(20000, 8.0, seed=5)),
          ("pipe", "PIPE", workloads.pipe_flow(5000, seed=4))]
 for name, mode, (params, st) in cases:
     s = B200SPHStrategy(params, SphConstants(mode=mode))
