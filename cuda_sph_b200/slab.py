@@ -437,7 +437,7 @@ class GpuSlabRunner(SlabRunner):
 
 def plan_capacities(col_hist, bounds: Sequence[int], rank: int, n_global: int, pipe_mode: bool, *,
                     own_slack: float = 1.08, ghost_slack: float = 1.4, migrant_frac: float = 0.02,
-                    far_frac: float = 0.005) -> dict:
+                    far_frac: float = 0.005, migrant_floor: int = 4096) -> dict:
     """Slot and block capacities of rank `rank` for the native exchange, derived from the GLOBAL column histogram of the
     start state so that every rank computes the same block sizes: the block rank a sends to rank b has the size of the
     block b sends to a (an all_to_all with static split sizes needs that).
@@ -452,7 +452,7 @@ def plan_capacities(col_hist, bounds: Sequence[int], rank: int, n_global: int, p
     assert len(hist) == bounds[-1] and bounds[0] == 0
     own = [int(hist[bounds[r]:bounds[r + 1]].sum()) for r in range(world)]
     per_rank = max(max(own), n_global // world)
-    m_adj = int(migrant_frac * per_rank) + 4096
+    m_adj = int(migrant_frac * per_rank) + int(migrant_floor)
 
     def band(r, side):   # particles rank r sends as ghosts to its left (0) / right (1) neighbour at the start
         lo, hi = bounds[r], bounds[r + 1]
@@ -495,7 +495,8 @@ class NativeSlabRunner:
 
     def __init__(self, params, constants=None, *, col_hist: np.ndarray, bounds: Sequence[int], device: int = 0,
                  group=None, own_slack: float = 1.08, ghost_slack: float = 1.4, migrant_frac: float = 0.02,
-                 far_frac: float = 0.005, compact_every: int = 4, poll_every: int = 16, p2p: bool | None = None):
+                 far_frac: float = 0.005, compact_every: int = 4, poll_every: int = 16, p2p: bool | None = None,
+                 migrant_floor: int = 4096):
         from . import _lib
         from .strategy import SphConstants
         self._lib = _lib.load()
@@ -504,7 +505,7 @@ class NativeSlabRunner:
         # what rebalanced() needs to build the successor of this runner
         self._ctor = dict(params=params, constants=constants, device=device, group=group, own_slack=own_slack,
                           ghost_slack=ghost_slack, migrant_frac=migrant_frac, far_frac=far_frac,
-                          compact_every=compact_every, poll_every=poll_every, p2p=p2p)
+                          compact_every=compact_every, poll_every=poll_every, p2p=p2p, migrant_floor=migrant_floor)
         self.group = group
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -526,7 +527,8 @@ class NativeSlabRunner:
         pipe_mode = cst.mode.upper() == "PIPE"
 
         plan = plan_capacities(col_hist, self.bounds, self.rank, self.n_global, pipe_mode, own_slack=own_slack,
-                               ghost_slack=ghost_slack, migrant_frac=migrant_frac, far_frac=far_frac)
+                               ghost_slack=ghost_slack, migrant_frac=migrant_frac, far_frac=far_frac,
+                               migrant_floor=migrant_floor)
         cap_m, cap_g = plan["cap_m"], plan["cap_g"]
         self.own_cap, self.capacity = plan["own_cap"], plan["capacity"]
 
@@ -572,7 +574,8 @@ class NativeSlabRunner:
             err = None
             try:
                 self._open_peers(col_hist, pipe_mode, dict(own_slack=own_slack, ghost_slack=ghost_slack,
-                                                           migrant_frac=migrant_frac, far_frac=far_frac), dev)
+                                                           migrant_frac=migrant_frac, far_frac=far_frac,
+                                                           migrant_floor=migrant_floor), dev)
             except Exception as exc:   # noqa: BLE001 -- reported below, then agreed on by all ranks
                 err = exc
             ok = torch.tensor([0 if err else 1], device=dev, dtype=torch.int32)

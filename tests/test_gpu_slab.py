@@ -118,6 +118,55 @@ def test_two_gpu_rebalance_continues_bitwise(tmp_path):
     assert eq(got["pos"], ref.position) and eq(got["vel"], ref.velocity) and eq(got["rho"], ref.density)
 
 
+def _overflow_worker(rank, world, port, n, out_path):
+    import faulthandler
+    import torch.distributed as dist
+    faulthandler.dump_traceback_later(150, exit=True)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from cuda_sph_b200 import SphConstants, workloads
+        from cuda_sph_b200.slab import NativeSlabRunner, equal_count_bounds
+        params, st = workloads.uniform_box(n, 8.0, seed=21)
+        n_cols = int(np.ceil(params.space_size[0] / params.voxel_size[0]))
+        cols = np.clip((st.position[:, 0] / params.voxel_size[0]).astype(np.int64), 0, n_cols - 1)
+        hist = np.bincount(cols, minlength=n_cols)
+        # migrant blocks of 8 records: the first step already has hundreds of migrants per direction
+        run = NativeSlabRunner(params, SphConstants(mode="BOX"), col_hist=hist, bounds=equal_count_bounds(hist, world),
+                               device=rank, migrant_frac=0.0, migrant_floor=8, own_slack=2.0, poll_every=0)
+        run.load_global(st.position, st.velocity)
+        run.step(2)
+        stt = run.status()
+        tot = torch.tensor([stt["live"], stt["overflow"] & 1], dtype=torch.int64, device=f"cuda:{rank}")
+        dist.all_reduce(tot)
+        raised = False
+        try:
+            run.check()
+        except RuntimeError:
+            raised = True
+        if rank == 0:
+            np.savez(out_path, live=int(tot[0]), overflowed=int(tot[1]), raised=raised)
+        run.close()
+    finally:
+        faulthandler.cancel_dump_traceback_later()
+        dist.destroy_process_group()
+
+
+def test_two_gpu_migrant_overflow_keeps_the_particles(tmp_path):
+    """a migrant whose record does not fit its send block must not vanish.  With 8-record migrant blocks the
+    exchange overflows at once: the flag is raised (sticky, check() raises on every rank) and every particle is still
+    owned by somebody -- the sender keeps what it could not send and retries in the next step."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    n, out = 200000, str(tmp_path / "overflow.npz")
+    mp.spawn(_overflow_worker, args=(2, _free_port(), n, out), nprocs=2, join=True)
+    got = np.load(out)
+    assert int(got["overflowed"]) > 0 and bool(got["raised"])
+    assert int(got["live"]) == n
+
+
 def _case(mode, n):
     from cuda_sph_b200 import config, workloads
     if mode == "BOX":
