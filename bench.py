@@ -26,7 +26,8 @@ device-to-device copy outside the timed events).  `--window 0` disables that and
            H2D + step + D2H every step; copies interleaved with the step on two streams), wall clock around the
            synchronous calls.
 `roofline`: dominant kernel (the density sweep), algorithmic bytes / CUDA-event duration vs MEASURED_PEAKS.json, its
-           measured DRAM traffic (ncu, profiles/traffic.json) and the issue-slot roofline that actually binds it.
+           measured DRAM traffic (ncu, profiles/traffic.json) and the two roofs that actually bind it: shared-memory
+           wavefronts (the LSU data pipe) and issue slots.
 `cpu_baseline`: the oracle port timed on this box's host cores on a bounded sample of the same workload.
 """
 from __future__ import annotations
@@ -333,7 +334,7 @@ def measure_single(name, args, local_rank, stream, flush, *, K, W, e2e_steps, wi
     stage_bytes = dict(BYTES, sort=sort_bytes(passes))
     stage_gbs = {k_: stage_bytes[k_] * n / (stage_ms[k_] * 1e-3) / 1e9 for k_ in stage_ms}
     dom = max(stage_ms, key=stage_ms.get)
-    traffic, issue = None, None
+    traffic, issue, lsu = None, None, None
     try:   # measured DRAM bytes per launch of the dominant kernel, from the committed ncu capture of this workload
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(name)
         if tj and tj["particles"] == n and dom in tj:
@@ -346,12 +347,21 @@ def measure_single(name, args, local_rank, stream, flush, *, K, W, e2e_steps, wi
                 issue = {"warp_inst_per_launch": tj[dom]["warp_inst"], "achieved_ginst_s": rate / 1e9,
                          "peak_ginst_s": peak_issue / 1e9, "frac": rate / peak_issue,
                          "peak_source": "148 SMs x 4 issue slots x 1.965 GHz"}
+            if "smem_wavefronts" in tj[dom]:
+                # third roof, the one that binds the sweeps first: shared-memory wavefronts per launch (ncu) / live kernel
+                # time vs one wavefront per SM and cycle (the LSU data pipe)
+                peak_wf = 148 * 1.965e9
+                wrate = tj[dom]["smem_wavefronts"] / (stage_ms[dom] * 1e-3)
+                lsu = {"smem_wavefronts_per_launch": tj[dom]["smem_wavefronts"], "achieved_gwavefronts_s": wrate / 1e9,
+                       "peak_gwavefronts_s": peak_wf / 1e9, "frac": wrate / peak_wf,
+                       "peak_source": "148 SMs x 1 wavefront per cycle x 1.965 GHz"}
     except Exception:
         pass
     kname = {"density": "density_flat_kernel", "force": "force_rows_kernel"}.get(dom, dom + "_kernel")
     roofline = {"bound": "hbm", "kernel": kname, "achieved": stage_gbs[dom], "peak": hbm_peak,
                 "unit": "GB/s", "frac": stage_gbs[dom] / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": stage_bytes[dom] * n, "issue_roofline": issue,
+                "shared_memory_roofline": lsu,
                 "algorithmic_bytes_per_particle": stage_bytes[dom], "kernel_ms": stage_ms[dom],
                 "stages_ms": stage_ms, "stages_gbs": stage_gbs,
                 "step_bytes_per_particle": sum(stage_bytes.values()),
